@@ -1,0 +1,508 @@
+// elementwise.cu — the HBM-bound kernels of the path: GroupNorm (two-source, +SiLU), LayerNorm, casts/upsample,
+// row softmax, transpose, fused CFG + scheduler step, time embedding, ConvTranspose1d overlap-add, tanh->int16.
+// All are coalesced / 16-byte vectorised along the contiguous channel dimension; statistics in fp32/fp64.
+// See include/tango_b200.h for the reference call sites each entry point replaces.
+#include "tng_ptx.cuh"
+#include "tng_internal.h"
+
+namespace tng {
+
+__device__ __forceinline__ float4 load4(const void* base, int dt, long long idx) {
+  if (dt == TNG_DT_F32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+  const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store4_bf16(__nv_bfloat16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16(v.x, v.y);
+  u.y = pack_bf16(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float bf16_lo(float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ void store4_split(__nv_bfloat16* p, float4 v, int split_off) {
+  store4_bf16(p, v);
+  if (split_off > 0) store4_bf16(p + split_off, make_float4(bf16_lo(v.x), bf16_lo(v.y), bf16_lo(v.z), bf16_lo(v.w)));
+}
+__device__ __forceinline__ float act_f(float x, int act, float p) {
+  if (act == TNG_ACT_SILU) return silu_f(x);
+  if (act == TNG_ACT_LRELU) return x > 0.f ? x : x * p;
+  return x;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+constexpr int GN_ROWS = 64;  // pixels per CTA
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(const void* x0, int dt0, int C0, const void* x1, int dt1, int C1,
+                                                        long long HW, int groups, double* stats) {
+  __shared__ double s_sum[64], s_sq[64];
+  const int n = blockIdx.y;
+  const long long r0 = static_cast<long long>(blockIdx.x) * GN_ROWS;
+  const int C = C0 + C1;
+  const int cpg = C / groups;
+  if (threadIdx.x < groups) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+  __syncthreads();
+  const int nrows = static_cast<int>((HW - r0) < GN_ROWS ? (HW - r0) : GN_ROWS);
+  for (int q = threadIdx.x; q < C / 4; q += blockDim.x) {
+    const int c = q * 4;
+    const bool first = c < C0;
+    const void* base = first ? x0 : x1;
+    const int dt = first ? dt0 : dt1;
+    const int Cs = first ? C0 : C1;
+    const int cc = first ? c : c - C0;
+    float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    for (int r = 0; r < nrows; ++r) {
+      const float4 v = load4(base, dt, (n * HW + r0 + r) * Cs + cc);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cpg;
+      atomicAdd(&s_sum[g], static_cast<double>(s[j]));
+      atomicAdd(&s_sq[g], static_cast<double>(ss[j]));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    atomicAdd(&stats[(static_cast<long long>(n) * groups + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
+    atomicAdd(&stats[(static_cast<long long>(n) * groups + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, int C0, const void* x1, int dt1, int C1,
+                                                        long long HW, int groups, const double* stats,
+                                                        const float* gamma, const float* beta, float eps, int act,
+                                                        __nv_bfloat16* y, long long ld_y, int split_off,
+                                                        __nv_bfloat16* raw, long long ld_raw, int raw_split_off) {
+  extern __shared__ float s_ab[];  // scale[C], shift[C]
+  const int n = blockIdx.y;
+  const int C = C0 + C1;
+  const int cpg = C / groups;
+  float* s_scale = s_ab;
+  float* s_shift = s_ab + C;
+  const double cnt = static_cast<double>(HW) * cpg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double sum = stats[(static_cast<long long>(n) * groups + g) * 2 + 0];
+    const double sq = stats[(static_cast<long long>(n) * groups + g) * 2 + 1];
+    const double mean = sum / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = rstd * gamma[c];
+    s_scale[c] = sc;
+    s_shift[c] = beta[c] - static_cast<float>(mean) * sc;
+  }
+  __syncthreads();
+  const long long r0 = static_cast<long long>(blockIdx.x) * GN_ROWS;
+  const int nrows = static_cast<int>((HW - r0) < GN_ROWS ? (HW - r0) : GN_ROWS);
+  const int Q = C / 4;
+  for (int i = threadIdx.x; i < nrows * Q; i += blockDim.x) {
+    const int r = i / Q, q = i - r * Q;
+    const int c = q * 4;
+    const long long row = n * HW + r0 + r;
+    const bool first = c < C0;
+    const float4 v = first ? load4(x0, dt0, row * C0 + c) : load4(x1, dt1, row * C1 + (c - C0));
+    float4 o;
+    o.x = act_f(v.x * s_scale[c] + s_shift[c], act, 0.f);
+    o.y = act_f(v.y * s_scale[c + 1] + s_shift[c + 1], act, 0.f);
+    o.z = act_f(v.z * s_scale[c + 2] + s_shift[c + 2], act, 0.f);
+    o.w = act_f(v.w * s_scale[c + 3] + s_shift[c + 3], act, 0.f);
+    store4_split(y + row * ld_y + c, o, split_off);
+    if (raw) store4_split(raw + row * ld_raw + c, v, raw_split_off);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// one warp per row; the row is cached in registers (C <= 2048) so the variance is the exact two-pass form.
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long long rows, int C, const float* gamma,
+                                                         const float* beta, float eps, __nv_bfloat16* y, long long ld_y,
+                                                         int split_off) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int Q = C / 4;
+  float4 v[16];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int q = lane + i * 32;
+    if (q < Q) {
+      v[i] = *reinterpret_cast<const float4*>(x + row * C + q * 4);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int q = lane + i * 32;
+    if (q < Q) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / C + eps);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int q = lane + i * 32;
+    if (q < Q) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + q * 4));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + q * 4));
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      store4_split(y + row * ld_y + q * 4, o, split_off);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cast / upsample
+__global__ void __launch_bounds__(256) cast_act_kernel(const float* x, long long NB, int H, int W, int C, long long ld_x,
+                                                        int up, int act, float act_param, __nv_bfloat16* y,
+                                                        long long ld_y, int split_off) {
+  const int Ho = up ? 2 * H : H, Wo = up ? 2 * W : W;
+  const int Q = C / 4;
+  const long long total = NB * Ho * Wo * Q;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % Q);
+    const long long orow = i / Q;
+    long long irow = orow;
+    if (up) {
+      const int wo = static_cast<int>(orow % Wo);
+      const int ho = static_cast<int>((orow / Wo) % Ho);
+      const long long n = orow / (static_cast<long long>(Wo) * Ho);
+      irow = (n * H + (ho >> 1)) * W + (wo >> 1);
+    }
+    float4 v = *reinterpret_cast<const float4*>(x + irow * ld_x + q * 4);
+    v.x = act_f(v.x, act, act_param); v.y = act_f(v.y, act, act_param);
+    v.z = act_f(v.z, act, act_param); v.w = act_f(v.w, act, act_param);
+    store4_split(y + orow * ld_y + q * 4, v, split_off);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ row softmax
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* x, int L, long long ld_x, float scale,
+                                                            __nv_bfloat16* y, long long ld_y, int split_off) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const long long row = blockIdx.x;
+  const float* xr = x + row * ld_x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, xr[i] * scale);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
+    bc = t;
+  }
+  __syncthreads();
+  m = bc;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) s += expf(xr[i] * scale - m);
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    bc = t;
+  }
+  __syncthreads();
+  const float inv = 1.0f / bc;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const float p = expf(xr[i] * scale - m) * inv;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(p);
+    y[row * ld_y + i] = hi;
+    if (split_off > 0) y[row * ld_y + split_off + i] = __float2bfloat16_rn(p - __bfloat162float(hi));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ transpose
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* x, int R, int C, long long ld_x,
+                                                              __nv_bfloat16* y, long long ld_y) {
+  __shared__ __nv_bfloat16 t[32][33];
+  const long long b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    t[j][tx] = (r < R && c < C) ? x[(b * R + r) * ld_x + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (c < C && r < R) y[(b * C + c) * ld_y + r] = t[tx][j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ CFG + scheduler
+__global__ void __launch_bounds__(256) sched_step_kernel(const float* mo, long long ld_mo, int cfg, float guidance,
+                                                          const float* sample, const float* noise, const float* coef,
+                                                          float* prev, __nv_bfloat16* next_in, long long ld_in,
+                                                          int split_off, long long B, int C, long long HW) {
+  const float c_x0_s = coef[0], c_x0_m = coef[1], c_prev_x0 = coef[2], c_prev_s = coef[3], c_noise = coef[4];
+  const float c_eps_s = coef[5], c_eps_m = coef[6], c_prev_eps = coef[7], clip = coef[8], c_x0_div = coef[9];
+  const long long total = B * HW * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long hw = (i / C) % HW;
+    const long long b = i / (C * HW);
+    const long long nchw = (b * C + c) * HW + hw;
+    const float s = sample[nchw];
+    float out = s;
+    if (mo) {
+      float v;
+      if (cfg) {
+        const float u = mo[(b * HW + hw) * ld_mo + c];
+        const float t = mo[((B + b) * HW + hw) * ld_mo + c];
+        v = __fadd_rn(u, __fmul_rn(guidance, __fsub_rn(t, u)));  // models.py:246, no fma contraction
+      } else {
+        v = mo[(b * HW + hw) * ld_mo + c];
+      }
+      // scheduling_ddpm.py:306-311 / scheduling_ddim.py:303-313 with host-computed fp32 coefficients; the
+      // multiplications and additions keep the reference's association order (no fma contraction).
+      float x0 = __fdiv_rn(__fadd_rn(__fmul_rn(c_x0_s, s), __fmul_rn(c_x0_m, v)), c_x0_div);
+      if (clip > 0.f) x0 = fminf(fmaxf(x0, -clip), clip);
+      out = __fadd_rn(__fmul_rn(c_prev_x0, x0), __fmul_rn(c_prev_s, s));
+      if (c_prev_eps != 0.f) {
+        const float eps = __fadd_rn(__fmul_rn(c_eps_s, s), __fmul_rn(c_eps_m, v));
+        out = __fadd_rn(out, __fmul_rn(c_prev_eps, eps));
+      }
+      if (noise && c_noise != 0.f) out = __fadd_rn(out, __fmul_rn(c_noise, noise[nchw]));
+    }
+    if (prev) prev[nchw] = out;
+    if (next_in) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(out);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(out - __bfloat162float(hi));
+      const long long r0 = (b * HW + hw) * ld_in + c;
+      next_in[r0] = hi;
+      if (split_off > 0) next_in[r0 + split_off] = lo;
+      if (cfg) {
+        const long long r1 = ((B + b) * HW + hw) * ld_in + c;
+        next_in[r1] = hi;
+        if (split_off > 0) next_in[r1 + split_off] = lo;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ time embedding
+__global__ void timestep_embedding_kernel(const float* t, long long n, int dim, int flip, float freq_shift, float* out) {
+  const int half = dim / 2;
+  const long long total = n * half;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i % half);
+    const long long r = i / half;
+    // embeddings.py:44-51: exponent = (-log(10000) * arange(half)) / (half - shift); emb = t * exp(exponent)
+    const float exponent = __fdiv_rn(__fmul_rn(-9.210340371976184f, static_cast<float>(j)),
+                                     static_cast<float>(half) - freq_shift);
+    const float e = __fmul_rn(t[r], expf(exponent));
+    const float sv = sinf(e), cv = cosf(e);
+    float* o = out + r * dim;
+    if (flip) { o[j] = cv; o[half + j] = sv; } else { o[j] = sv; o[half + j] = cv; }
+    if ((dim & 1) && j == 0) o[dim - 1] = 0.f;
+  }
+}
+
+// y[m, n] = post(sum_k pre(x[m,k]) * w[n,k] + b[n]); one warp per output element (tiny, exact fp32).
+__global__ void __launch_bounds__(256) linear_f32_kernel(const float* x, long long M, int K, const float* w,
+                                                          const float* b, int N, int pre_act, int post_act, float* y) {
+  const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= M * N) return;
+  const long long m = wid / N;
+  const int n = static_cast<int>(wid % N);
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc += act_f(x[m * K + k], pre_act, 0.f) * w[static_cast<long long>(n) * K + k];
+  acc = warp_sum(acc);
+  if (lane == 0) y[m * N + n] = act_f(acc + (b ? b[n] : 0.f), post_act, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------ ConvTranspose1d
+__global__ void __launch_bounds__(256) convt_gather_kernel(const float* Y, long long B, long long Lin, int ktaps, int Cout,
+                                                            int stride, int pad, long long Lout, const float* bias,
+                                                            float* y) {
+  const int Q = Cout / 4;
+  const long long total = B * Lout * Q;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % Q);
+    const long long l = (i / Q) % Lout;
+    const long long b = i / (Q * Lout);
+    float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias + q * 4)) : make_float4(0, 0, 0, 0);
+    // l = qi*stride + t - pad  =>  t = l + pad - qi*stride in [0, ktaps)
+    long long qi_hi = (l + pad) / stride;
+    if (qi_hi > Lin - 1) qi_hi = Lin - 1;
+    for (long long qi = qi_hi; qi >= 0; --qi) {
+      const long long t = l + pad - qi * stride;
+      if (t >= ktaps) break;
+      const float4 v = *reinterpret_cast<const float4*>(Y + ((b * Lin + qi) * ktaps + t) * Cout + q * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(y + (b * Lout + l) * Cout + q * 4) = acc;
+  }
+}
+
+__global__ void tanh_to_i16_kernel(const float* x, long long n, long long ld_x, float* wf, int16_t* wi) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float t = tanhf(x[i * ld_x]);
+    if (wf) wf[i] = t;
+    // hifigan/utilities.py:81: (wavs.cpu().numpy() * 32768).astype("int16") — float32 product, C cast toward
+    // zero through int32 then wrap to int16 (tanh == 1.0 wraps to -32768, as in the reference).
+    if (wi) wi[i] = static_cast<int16_t>(__float2int_rz(__fmul_rn(t, 32768.0f)));
+  }
+}
+
+static inline int grid_for(long long total, int block = 256) {
+  long long g = (total + block - 1) / block;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace tng
+
+using namespace tng;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int tng_groupnorm_stats(const void* x0, int32_t dt0, int64_t C0, const void* x1, int32_t dt1, int64_t C1,
+                                   int64_t NB, int64_t HW, int32_t groups, double* stats, void* stream) {
+  const int64_t C = C0 + (x1 ? C1 : 0);
+  if (!x0 || !stats || groups <= 0 || groups > 64 || C % groups || C0 % 4 || (x1 && C1 % 4))
+    return set_error(TNG_EINVAL, "groupnorm_stats: bad shape C0=%lld C1=%lld groups=%d", (long long)C0, (long long)C1, groups);
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * NB * groups, ST(stream));
+  if (e != cudaSuccess) return set_error(TNG_ECUDA, "memset: %s", cudaGetErrorString(e));
+  dim3 grid((unsigned)((HW + GN_ROWS - 1) / GN_ROWS), (unsigned)NB);
+  gn_stats_kernel<<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, x1, dt1, x1 ? (int)C1 : 0, HW, groups, stats);
+  count_launch();
+  return check_launch("gn_stats");
+}
+
+extern "C" int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, const void* x1, int32_t dt1, int64_t C1,
+                                   int64_t NB, int64_t HW, int32_t groups, const double* stats, const float* gamma,
+                                   const float* beta, float eps, int32_t act, void* y, int64_t ld_y, int32_t split_off,
+                                   void* raw_bf16, int64_t ld_raw, int32_t raw_split_off, void* stream) {
+  const int64_t C = C0 + (x1 ? C1 : 0);
+  if (!x0 || !stats || !y || C % groups || C0 % 4 || (x1 && C1 % 4) || ld_y % 4 || split_off % 4 || C > 8192)
+    return set_error(TNG_EINVAL, "groupnorm_apply: bad shape");
+  dim3 grid((unsigned)((HW + GN_ROWS - 1) / GN_ROWS), (unsigned)NB);
+  const size_t smem = sizeof(float) * 2 * C;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    attr = true;
+  }
+  gn_apply_kernel<<<grid, 256, smem, ST(stream)>>>(x0, dt0, (int)C0, x1, dt1, x1 ? (int)C1 : 0, HW, groups, stats, gamma,
+                                                    beta, eps, act, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off,
+                                                    reinterpret_cast<__nv_bfloat16*>(raw_bf16), ld_raw, raw_split_off);
+  count_launch();
+  return check_launch("gn_apply");
+}
+
+extern "C" int tng_layernorm(const float* x, int64_t rows, int64_t C, const float* gamma, const float* beta, float eps,
+                             void* y, int64_t ld_y, int32_t split_off, void* stream) {
+  if (!x || !y || C % 4 || C > 2048 || ld_y % 4 || split_off % 4) return set_error(TNG_EINVAL, "layernorm: C=%lld unsupported", (long long)C);
+  const int wpb = 8;
+  layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, ST(stream)>>>(
+      x, rows, (int)C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off);
+  count_launch();
+  return check_launch("layernorm");
+}
+
+extern "C" int tng_cast_act(const float* x, int64_t NB, int64_t H, int64_t W, int64_t C, int64_t ld_x,
+                            int32_t upsample2x, int32_t act, float act_param, void* y, int64_t ld_y, int32_t split_off,
+                            void* stream) {
+  if (!x || !y || C % 4 || ld_x % 4 || ld_y % 4 || split_off % 4) return set_error(TNG_EINVAL, "cast_act: bad shape");
+  const long long total = NB * H * W * (upsample2x ? 4 : 1) * (C / 4);
+  cast_act_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(x, NB, (int)H, (int)W, (int)C, ld_x, upsample2x, act, act_param,
+                                                            reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off);
+  count_launch();
+  return check_launch("cast_act");
+}
+
+extern "C" int tng_softmax_rows(const float* x, int64_t rows, int64_t L, int64_t ld_x, float scale, void* y,
+                                int64_t ld_y, int32_t split_off, void* stream) {
+  if (!x || !y || rows <= 0 || L <= 0) return set_error(TNG_EINVAL, "softmax_rows: bad shape");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(x, (int)L, ld_x, scale, reinterpret_cast<__nv_bfloat16*>(y),
+                                                               ld_y, split_off);
+  count_launch();
+  return check_launch("softmax_rows");
+}
+
+extern "C" int tng_transpose_bf16(const void* x, int64_t B, int64_t R, int64_t C, int64_t ld_x, void* y, int64_t ld_y,
+                                  void* stream) {
+  if (!x || !y) return set_error(TNG_EINVAL, "transpose: null");
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)B);
+  transpose_bf16_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), (int)R, (int)C, ld_x,
+                                                       reinterpret_cast<__nv_bfloat16*>(y), ld_y);
+  count_launch();
+  return check_launch("transpose");
+}
+
+extern "C" int tng_sched_step(const float* model_out, int64_t ld_mo, int32_t cfg, float guidance, const float* sample,
+                              const float* noise, const float* coef, float* prev, void* next_in, int64_t ld_in,
+                              int32_t split_off, int64_t B, int64_t C, int64_t HW, void* stream) {
+  if (!sample || !coef || (!prev && !next_in)) return set_error(TNG_EINVAL, "sched_step: null argument");
+  sched_step_kernel<<<grid_for(B * C * HW), 256, 0, ST(stream)>>>(model_out, ld_mo, cfg, guidance, sample, noise, coef, prev,
+                                                                  reinterpret_cast<__nv_bfloat16*>(next_in), ld_in,
+                                                                  split_off, B, (int)C, HW);
+  count_launch();
+  return check_launch("sched_step");
+}
+
+extern "C" int tng_timestep_embedding(const float* t, int64_t n, int32_t dim, int32_t flip_sin_to_cos, float freq_shift,
+                                      float* out, void* stream) {
+  if (!t || !out || dim < 2) return set_error(TNG_EINVAL, "timestep_embedding: bad argument");
+  timestep_embedding_kernel<<<grid_for(n * (dim / 2)), 256, 0, ST(stream)>>>(t, n, dim, flip_sin_to_cos, freq_shift, out);
+  count_launch();
+  return check_launch("timestep_embedding");
+}
+
+extern "C" int tng_linear_f32(const float* x, int64_t M, int64_t K, const float* w, const float* b, int64_t N,
+                              int32_t pre_act, int32_t post_act, float* y, void* stream) {
+  if (!x || !w || !y) return set_error(TNG_EINVAL, "linear_f32: null");
+  const long long threads = M * N * 32;
+  linear_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ST(stream)>>>(x, M, (int)K, w, b, (int)N, pre_act, post_act, y);
+  count_launch();
+  return check_launch("linear_f32");
+}
+
+extern "C" int tng_convt_gather(const float* Y, int64_t B, int64_t Lin, int32_t ktaps, int64_t Cout, int32_t stride,
+                                int32_t pad, int64_t Lout, const float* bias, float* y, void* stream) {
+  if (!Y || !y || Cout % 4) return set_error(TNG_EINVAL, "convt_gather: bad shape");
+  convt_gather_kernel<<<grid_for(B * Lout * (Cout / 4)), 256, 0, ST(stream)>>>(Y, B, Lin, ktaps, (int)Cout, stride, pad, Lout,
+                                                                               bias, y);
+  count_launch();
+  return check_launch("convt_gather");
+}
+
+extern "C" int tng_tanh_to_i16(const float* x, int64_t n, int64_t ld_x, float* wave_f32, int16_t* wave_i16, void* stream) {
+  if (!x) return set_error(TNG_EINVAL, "tanh_to_i16: null");
+  tanh_to_i16_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(x, n, ld_x, wave_f32, wave_i16);
+  count_launch();
+  return check_launch("tanh_to_i16");
+}

@@ -1,0 +1,292 @@
+"""ctypes binding of libtango_b200.so (include/tango_b200.h) + thin torch-tensor helpers.
+
+PyTorch is plumbing only here: it owns device memory and the current CUDA stream; every compute call goes
+through the C ABI into the hand-written sm_100a kernels. There is no CPU / eager fallback: if the library is
+missing or a call fails, a TangoB200Error is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+from . import build as _build
+
+ACT_NONE, ACT_SILU, ACT_LRELU, ACT_GEGLU = 0, 1, 2, 3
+DT_F32, DT_BF16 = 0, 1
+MAX_AVIEWS, MAX_KGROUPS = 4, 40
+
+# every symbol include/tango_b200.h declares (tests/test_cabi.py checks the exports against the header)
+SYMBOLS = [
+    "tng_version", "tng_last_error", "tng_launch_count", "tng_conv_gemm", "tng_attention",
+    "tng_groupnorm_stats", "tng_groupnorm_apply", "tng_layernorm", "tng_cast_act", "tng_softmax_rows",
+    "tng_transpose_bf16", "tng_sched_step", "tng_timestep_embedding", "tng_linear_f32", "tng_convt_gather",
+    "tng_tanh_to_i16",
+]
+
+
+class TangoB200Error(RuntimeError):
+    pass
+
+
+class AView(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("C", C.c_int64), ("W", C.c_int64), ("H", C.c_int64), ("NB", C.c_int64),
+                ("s_w", C.c_int64), ("s_h", C.c_int64), ("s_n", C.c_int64)]
+
+
+class KGroup(C.Structure):
+    _fields_ = [("view", C.c_int32), ("a_c0", C.c_int32), ("dw", C.c_int32), ("dh", C.c_int32),
+                ("b_k0", C.c_int32), ("nkb", C.c_int32)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", AView * MAX_AVIEWS), ("n_aviews", C.c_int32),
+        ("b", C.c_void_p), ("Ncols", C.c_int64), ("Ktot", C.c_int64),
+        ("W", C.c_int32), ("H", C.c_int32), ("NB", C.c_int32),
+        ("g", KGroup * MAX_KGROUPS), ("n_groups", C.c_int32),
+        ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("res", C.c_void_p), ("res_dtype", C.c_int32),
+        ("ldr", C.c_int64), ("alpha", C.c_float), ("accumulate", C.c_int32),
+        ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int64),
+        ("act", C.c_int32), ("act_param", C.c_float), ("split_off", C.c_int32), ("block_n", C.c_int32),
+    ]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ld_q", C.c_int64), ("q_col0", C.c_int32), ("q_lo_off", C.c_int32),
+        ("k", C.c_void_p), ("ld_k", C.c_int64), ("k_col0", C.c_int32), ("k_lo_off", C.c_int32),
+        ("v", C.c_void_p), ("ld_v", C.c_int64), ("v_col0", C.c_int32), ("v_lo_off", C.c_int32),
+        ("kbias", C.c_void_p), ("out", C.c_void_p), ("ld_o", C.c_int64), ("split_off", C.c_int32),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32),
+        ("scale", C.c_float), ("nsplit", C.c_int32),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen libtango_b200.so (building it in-tree first if it is absent and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise TangoB200Error(f"{path} is missing: run `python -m tango_b200.build`")
+        _build.build()
+    lib = C.CDLL(path)
+    lib.tng_version.restype = C.c_int
+    lib.tng_last_error.restype = C.c_char_p
+    lib.tng_launch_count.restype = C.c_uint64
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    sigs = {
+        "tng_conv_gemm": [C.POINTER(GemmDesc), vp],
+        "tng_attention": [C.POINTER(AttnDesc), vp],
+        "tng_groupnorm_stats": [vp, i32, i64, vp, i32, i64, i64, i64, i32, vp, vp],
+        "tng_groupnorm_apply": [vp, i32, i64, vp, i32, i64, i64, i64, i32, vp, vp, vp, f32, i32, vp, i64, i32, vp,
+                                i64, i32, vp],
+        "tng_layernorm": [vp, i64, i64, vp, vp, f32, vp, i64, i32, vp],
+        "tng_cast_act": [vp, i64, i64, i64, i64, i64, i32, i32, f32, vp, i64, i32, vp],
+        "tng_softmax_rows": [vp, i64, i64, i64, f32, vp, i64, i32, vp],
+        "tng_transpose_bf16": [vp, i64, i64, i64, i64, vp, i64, vp],
+        "tng_sched_step": [vp, i64, i32, f32, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp],
+        "tng_timestep_embedding": [vp, i64, i32, i32, f32, vp, vp],
+        "tng_linear_f32": [vp, i64, i64, vp, vp, i64, i32, i32, vp, vp],
+        "tng_convt_gather": [vp, i64, i64, i32, i64, i32, i32, i64, vp, vp, vp],
+        "tng_tanh_to_i16": [vp, i64, i64, vp, vp, vp],
+    }
+    for name, argt in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argt
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().tng_last_error().decode("utf-8", "replace")
+        raise TangoB200Error(f"{what or 'tng call'} failed ({rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().tng_launch_count())
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return DT_F32
+    if t.dtype == torch.bfloat16:
+        return DT_BF16
+    raise TangoB200Error(f"unsupported dtype {t.dtype}")
+
+
+def require_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise TangoB200Error("tango_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+# --------------------------------------------------------------------------------------------------- conv / gemm
+class View:
+    """A bf16 channels-last activation view (img, h, w, c) with element strides."""
+
+    __slots__ = ("t", "C", "W", "H", "NB", "s_w", "s_h", "s_n", "off")
+
+    def __init__(self, t: torch.Tensor, C_: int, W: int, H: int, NB: int, s_w: int, s_h: int, s_n: int, off: int = 0):
+        self.t, self.C, self.W, self.H, self.NB = t, C_, W, H, NB
+        self.s_w, self.s_h, self.s_n, self.off = s_w, s_h, s_n, off
+
+    @staticmethod
+    def rows(t: torch.Tensor, NB: int, H: int, W: int, C_: Optional[int] = None) -> "View":
+        """t: contiguous bf16 [NB*H*W, ld]; the view exposes its first C_ (default ld) channels."""
+        ld = t.shape[-1]
+        return View(t, ld if C_ is None else C_, W, H, NB, ld, W * ld, H * W * ld)
+
+
+def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tensor, W: int, H: int, NB: int, *,
+              bias=None, rowvec=None, res=None, alpha: float = 1.0, accumulate: bool = False, out_f32=None,
+              out_bf16=None, act: int = ACT_NONE, act_param: float = 0.0, split_off: int = 0, block_n: int = 0,
+              ld_f32: Optional[int] = None, ld_bf16: Optional[int] = None, ldr: Optional[int] = None) -> None:
+    """Launch tng_conv_gemm. groups: (view, a_c0, dw, dh, b_k0, nkb). weight: bf16 [Ncols, Ktot]."""
+    lib = load()
+    d = GemmDesc()
+    require_cuda(weight, bias, rowvec, res, out_f32, out_bf16)
+    assert weight.dtype == torch.bfloat16 and weight.is_contiguous()
+    d.n_aviews = len(views)
+    for i, v in enumerate(views):
+        require_cuda(v.t)
+        assert v.t.dtype == torch.bfloat16
+        d.a[i] = AView(v.t.data_ptr() + 2 * v.off, v.C, v.W, v.H, v.NB, v.s_w, v.s_h, v.s_n)
+    d.b = weight.data_ptr()
+    d.Ncols, d.Ktot = weight.shape
+    d.W, d.H, d.NB = W, H, NB
+    d.n_groups = len(groups)
+    if len(groups) > MAX_KGROUPS:
+        raise TangoB200Error(f"{len(groups)} k-groups > {MAX_KGROUPS}")
+    for i, g in enumerate(groups):
+        d.g[i] = KGroup(*g)
+    d.bias = ptr(bias)
+    d.rowvec = ptr(rowvec)
+    d.res = ptr(res)
+    if res is not None:
+        d.res_dtype = _dt(res)
+        d.ldr = res.shape[-1] if ldr is None else ldr
+    d.alpha = alpha
+    d.accumulate = int(accumulate)
+    d.out_f32 = ptr(out_f32)
+    if out_f32 is not None:
+        d.ld_f32 = out_f32.shape[-1] if ld_f32 is None else ld_f32
+    d.out_bf16 = ptr(out_bf16)
+    if out_bf16 is not None:
+        d.ld_bf16 = out_bf16.shape[-1] if ld_bf16 is None else ld_bf16
+    d.act, d.act_param, d.split_off, d.block_n = act, act_param, split_off, block_n
+    check(lib.tng_conv_gemm(C.byref(d), stream_ptr()), "tng_conv_gemm")
+
+
+def attention(q, k, v, out, *, batch, heads, Lq, Lk, scale, q_col0=0, k_col0=0, v_col0=0, kbias=None, nsplit=1,
+              q_lo_off=0, k_lo_off=0, v_lo_off=0, split_off=0) -> None:
+    lib = load()
+    require_cuda(q, k, v, out, kbias)
+    d = AttnDesc()
+    d.q, d.ld_q, d.q_col0, d.q_lo_off = q.data_ptr(), q.shape[-1], q_col0, q_lo_off
+    d.k, d.ld_k, d.k_col0, d.k_lo_off = k.data_ptr(), k.shape[-1], k_col0, k_lo_off
+    d.v, d.ld_v, d.v_col0, d.v_lo_off = v.data_ptr(), v.shape[-1], v_col0, v_lo_off
+    d.kbias = ptr(kbias)
+    d.out, d.ld_o, d.split_off = out.data_ptr(), out.shape[-1], split_off
+    d.batch, d.heads, d.Lq, d.Lk, d.scale, d.nsplit = batch, heads, Lq, Lk, scale, nsplit
+    check(lib.tng_attention(C.byref(d), stream_ptr()), "tng_attention")
+
+
+# --------------------------------------------------------------------------------------------------- norms etc.
+def groupnorm(x0, x1, NB, HW, groups, stats, gamma, beta, eps, act, y, *, split_off=0, raw=None, raw_split_off=0):
+    """GroupNorm(+act) of the channel concat [x0 | x1] (x1 may be None) -> bf16 y; optional raw bf16 copy."""
+    lib = load()
+    require_cuda(x0, x1, stats, gamma, beta, y, raw)
+    C0 = x0.shape[-1]
+    C1 = 0 if x1 is None else x1.shape[-1]
+    s = stream_ptr()
+    check(lib.tng_groupnorm_stats(x0.data_ptr(), _dt(x0), C0, ptr(x1), 0 if x1 is None else _dt(x1), C1, NB, HW,
+                                  groups, stats.data_ptr(), s), "tng_groupnorm_stats")
+    check(lib.tng_groupnorm_apply(x0.data_ptr(), _dt(x0), C0, ptr(x1), 0 if x1 is None else _dt(x1), C1, NB, HW,
+                                  groups, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, act,
+                                  y.data_ptr(), y.shape[-1], split_off, ptr(raw),
+                                  0 if raw is None else raw.shape[-1], raw_split_off, s), "tng_groupnorm_apply")
+
+
+def layernorm(x, gamma, beta, eps, y, *, split_off=0):
+    require_cuda(x, gamma, beta, y)
+    rows, Cc = x.shape
+    check(load().tng_layernorm(x.data_ptr(), rows, Cc, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(),
+                               y.shape[-1], split_off, stream_ptr()), "tng_layernorm")
+
+
+def cast_act(x, NB, H, W, y, *, Cc=None, upsample2x=False, act=ACT_NONE, act_param=0.0, split_off=0):
+    require_cuda(x, y)
+    Cc = x.shape[-1] if Cc is None else Cc
+    check(load().tng_cast_act(x.data_ptr(), NB, H, W, Cc, x.shape[-1], int(upsample2x), act, act_param, y.data_ptr(),
+                              y.shape[-1], split_off, stream_ptr()), "tng_cast_act")
+
+
+def softmax_rows(x, scale, y, *, L=None, split_off=0):
+    require_cuda(x, y)
+    rows = x.shape[0]
+    L = x.shape[1] if L is None else L
+    check(load().tng_softmax_rows(x.data_ptr(), rows, L, x.shape[-1], scale, y.data_ptr(), y.shape[-1], split_off,
+                                  stream_ptr()), "tng_softmax_rows")
+
+
+def transpose_bf16(x, B, R, Cc, y):
+    require_cuda(x, y)
+    check(load().tng_transpose_bf16(x.data_ptr(), B, R, Cc, x.shape[-1], y.data_ptr(), y.shape[-1], stream_ptr()),
+          "tng_transpose_bf16")
+
+
+def sched_step(model_out, cfg, guidance, sample, noise, coef, prev, next_in, *, B, Cc, HW, split_off=0):
+    require_cuda(model_out, sample, noise, coef, prev, next_in)
+    check(load().tng_sched_step(ptr(model_out), 0 if model_out is None else model_out.shape[-1], int(cfg), guidance,
+                                sample.data_ptr(), ptr(noise), coef.data_ptr(), ptr(prev), ptr(next_in),
+                                0 if next_in is None else next_in.shape[-1], split_off, B, Cc, HW, stream_ptr()),
+          "tng_sched_step")
+
+
+def timestep_embedding(t, dim, flip_sin_to_cos, freq_shift, out):
+    require_cuda(t, out)
+    check(load().tng_timestep_embedding(t.data_ptr(), t.numel(), dim, int(flip_sin_to_cos), freq_shift,
+                                        out.data_ptr(), stream_ptr()), "tng_timestep_embedding")
+
+
+def linear_f32(x, w, b, y, *, pre_act=ACT_NONE, post_act=ACT_NONE):
+    require_cuda(x, w, b, y)
+    M, K = x.shape
+    N = w.shape[0]
+    check(load().tng_linear_f32(x.data_ptr(), M, K, w.data_ptr(), ptr(b), N, pre_act, post_act, y.data_ptr(),
+                                stream_ptr()), "tng_linear_f32")
+
+
+def convt_gather(Y, B, Lin, ktaps, Cout, stride, pad, Lout, bias, y):
+    require_cuda(Y, bias, y)
+    check(load().tng_convt_gather(Y.data_ptr(), B, Lin, ktaps, Cout, stride, pad, Lout, ptr(bias), y.data_ptr(),
+                                  stream_ptr()), "tng_convt_gather")
+
+
+def tanh_to_i16(x, n, ld_x, wave_f32, wave_i16):
+    require_cuda(x, wave_f32, wave_i16)
+    check(load().tng_tanh_to_i16(x.data_ptr(), n, ld_x, ptr(wave_f32), ptr(wave_i16), stream_ptr()),
+          "tng_tanh_to_i16")
