@@ -408,7 +408,7 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   memset(&p, 0, sizeof(p));
   p.W = d->W; p.H = d->H; p.NB = d->NB;
   // M tile = bw x bh x bn output pixels (product 128)
-  if (d->W >= BM || (d->H == 1 && d->NB == 1)) {
+  if (d->W >= BM || d->H == 1) {
     p.bw = BM; p.bh = 1; p.bn = 1;
   } else {
     if (!is_pow2(d->W)) return set_error(TNG_EINVAL, "W=%d < 128 must be a power of two", d->W);

@@ -1,0 +1,121 @@
+"""CPU: host-side logic of the product (no GPU compute): scheduler grids / coefficient tables against the oracle,
+weight packing, state_dict shapes, k-group construction, and that GPU-only entry points refuse CPU tensors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import schedulers as osched
+from tango_b200 import ops, synth
+from tango_b200 import schedulers as S
+
+
+def emulate_step(coef, v, s, noise):
+    """The arithmetic of tng_sched_step (elementwise.cu:sched_step_kernel) restated with torch CPU fp32 ops."""
+    c = [coef[i] for i in range(10)]
+    x0 = (c[0] * s + c[1] * v) / c[9]
+    if float(c[8]) > 0:
+        x0 = x0.clamp(-float(c[8]), float(c[8]))
+    out = c[2] * x0 + c[3] * s
+    if float(c[7]) != 0:
+        out = out + c[7] * (c[5] * s + c[6] * v)
+    if noise is not None and float(c[4]) != 0:
+        out = out + c[4] * noise
+    return out
+
+
+@pytest.mark.parametrize("n", [10, 100, 200])
+def test_timestep_grids_match_oracle(n):
+    d, o = S.DDPMScheduler.from_pretrained(), osched.OracleDDPM(**osched.SD21_CONFIG)
+    d.set_timesteps(n)
+    o.set_timesteps(n)
+    assert d.timesteps.dtype == torch.int64 and torch.equal(d.timesteps, o.timesteps)
+    di, oi = S.DDIMScheduler.from_pretrained(), osched.OracleDDIM(**osched.SD21_CONFIG)
+    di.set_timesteps(n)
+    oi.set_timesteps(n)
+    assert torch.equal(di.timesteps, oi.timesteps)
+    assert d.init_noise_sigma == 1.0 and d.order == 1
+    with pytest.raises(ValueError):
+        d.set_timesteps(1001)
+
+
+@pytest.mark.parametrize("pred", ["v_prediction", "epsilon"])
+def test_coefficient_tables_bit_exact_vs_oracle(pred):
+    g = torch.Generator().manual_seed(0)
+    s0 = torch.randn(2, 8, 16, 16, generator=g)
+    cfg = dict(osched.SD21_CONFIG, prediction_type=pred)
+    for n in (10, 200):
+        d = S.DDPMScheduler.from_pretrained(prediction_type=pred)
+        d.set_timesteps(n)
+        o = osched.OracleDDPM(**cfg)
+        o.set_timesteps(n)
+        tab = d.coefficient_table()
+        assert tab.shape == (n, S.NCOEF) and tab.dtype == torch.float32
+        x = s0.clone()
+        for i, t in enumerate(o.timesteps[:12]):
+            v = torch.sin(x * 2 + i)
+            nz = torch.randn(x.shape, generator=g)
+            ref = o.step(v, t, x, nz if int(t) > 0 else None)
+            got = emulate_step(tab[i], v, x, nz)
+            assert torch.equal(ref, got)
+            x = ref
+        # last step (t == 0): no noise
+        t = o.timesteps[-1]
+        assert torch.equal(o.step(x, t, x), emulate_step(tab[-1], x, x, None))
+        di = S.DDIMScheduler.from_pretrained(prediction_type=pred)
+        di.set_timesteps(n)
+        oi = osched.OracleDDIM(**cfg)
+        oi.set_timesteps(n)
+        tabi = di.coefficient_table()
+        x = s0.clone()
+        for i, t in enumerate(oi.timesteps[:12]):
+            v = torch.cos(x * 2 + i)
+            ref = oi.step(v, t, x)
+            assert torch.equal(ref, emulate_step(tabi[i], v, x, None))
+            x = ref
+
+
+def test_unet_shapes_and_param_count():
+    sh = synth.unet_param_shapes(synth.BASE_UNET_CONFIG)
+    assert len(sh) == 686
+    assert sum(int(np.prod(v)) for v in sh.values()) == 865_933_768
+    shx = synth.unet_param_shapes(synth.XL_UNET_CONFIG)
+    assert sum(int(np.prod(v)) for v in shx.values()) == 891_492_808
+    assert sh["down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k.weight"] == (320, 1024)
+    assert sh["up_blocks.1.resnets.0.conv_shortcut.weight"] == (1280, 2560, 1, 1)
+    assert len(synth.vae_decoder_param_shapes()) == 308
+
+
+def test_packed_conv_layout_and_groups():
+    w = torch.arange(4 * 8 * 9, dtype=torch.float32).reshape(4, 8, 3, 3) / 100
+    pc = ops.PackedConv(w, torch.zeros(4), split=False, device="cpu")
+    assert pc.weight.shape == (4, 72) and pc.weight.dtype == torch.bfloat16
+    # K index = tap * Cin + cin, tap = ky * 3 + kx
+    assert torch.equal(pc.weight[:, 3 * 8 + 2].float(), w[:, 2, 1, 0].to(torch.bfloat16).float())
+    g = pc.groups()
+    assert len(g) == 9 and g[0] == (0, 0, -1, -1, 0, 1) and g[8] == (0, 0, 1, 1, 64, 1)
+    pcs = ops.PackedConv(w, None, split=True, device="cpu")
+    assert pcs.weight.shape == (4, 144)
+    hi, lo = pcs.weight[:, :72].float(), pcs.weight[:, 72:].float()
+    assert (hi + lo - w.permute(0, 2, 3, 1).reshape(4, 72)).abs().max() < 5e-5
+    gs = pcs.groups(lo_views=[1])
+    assert len(gs) == 27 and gs[1][0] == 1 and gs[2][4] == 72
+    # stride 2: parity plane and plane offset per tap
+    w2 = torch.randn(64, 64, 3, 3)
+    p2 = ops.PackedConv(w2, None, split=False, device="cpu", stride=2)
+    g2 = p2.groups(parity_views=[0, 1, 2, 3])
+    assert g2[0][:4] == (3, 0, -1, -1) and g2[4][:4] == (0, 0, 0, 0) and g2[5][:4] == (1, 0, 0, 0)
+    # GEGLU interleave
+    wl = torch.arange(16 * 4, dtype=torch.float32).reshape(16, 4)
+    pg = ops.PackedConv(wl, torch.arange(16, dtype=torch.float32), split=False, device="cpu", geglu_bn=8)
+    assert pg.bias.tolist() == [0, 1, 2, 3, 8, 9, 10, 11, 4, 5, 6, 7, 12, 13, 14, 15]
+
+
+def test_no_cpu_fallback():
+    from tango_b200 import lib as L
+    x = torch.zeros(4, 8)
+    with pytest.raises(L.TangoB200Error):
+        L.layernorm(x, torch.ones(8), torch.zeros(8), 1e-5, torch.zeros(4, 8, dtype=torch.bfloat16))
+    d = S.DDPMScheduler.from_pretrained()
+    d.set_timesteps(10)
+    with pytest.raises(L.TangoB200Error):
+        d.step(torch.zeros(1, 8, 4, 4), 990, torch.zeros(1, 8, 4, 4))

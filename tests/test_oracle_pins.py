@@ -1,0 +1,142 @@
+"""CPU: pin the oracle (oracle/*.py) against (a) the golden vectors generated from the REAL reference by
+oracle/make_golden.py and (b) the known-answer constants of the diffusers fork's own tests
+(mustango/diffusers/tests/test_layers_utils.py:92-117, schedulers/test_scheduler_ddpm.py:62-131,
+schedulers/test_scheduler_ddim.py:46-54,94-122)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hifigan as ohifi
+from oracle import pipeline as opipe
+from oracle import schedulers as osched
+from oracle import unet as ounet
+from oracle import vae as ovae
+from tango_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def test_sinusoid_hardcoded():
+    t = torch.arange(128)
+    t1 = ounet.timestep_embedding(t, 64, flip_sin_to_cos=False, freq_shift=1)
+    t2 = ounet.timestep_embedding(t, 64, flip_sin_to_cos=True, freq_shift=0)
+    assert torch.allclose(t1[23:26, 47:50].flatten(),
+                          torch.tensor([0.9646, 0.9804, 0.9892, 0.9615, 0.9787, 0.9882, 0.9582, 0.9769, 0.9872]), 1e-3)
+    assert torch.allclose(t2[23:26, 47:50].flatten(),
+                          torch.tensor([0.3019, 0.2280, 0.1716, 0.3146, 0.2377, 0.1790, 0.3272, 0.2474, 0.1864]), 1e-3)
+
+
+def _dummy_sample_deter():
+    # mustango/diffusers/tests/schedulers/test_schedulers.py:236-247
+    n = 4 * 3 * 8 * 8
+    s = torch.arange(n).reshape(3, 8, 8, 4) / n
+    return s.permute(3, 0, 1, 2)
+
+
+def _dummy_model(sample, t):
+    return sample * t / (t + 1)
+
+
+@pytest.mark.parametrize("pred,exp_sum,exp_mean", [("epsilon", 258.9606, 0.3372), ("v_prediction", 202.0296, 0.2631)])
+def test_ddpm_full_loop_constants(pred, exp_sum, exp_mean):
+    s = osched.OracleDDPM(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                          clip_sample=True, prediction_type=pred)
+    sample = _dummy_sample_deter()
+    g = torch.manual_seed(0)
+    for t in reversed(range(1000)):
+        res = _dummy_model(sample, t)
+        noise = torch.randn(res.shape, generator=g) if t > 0 else None
+        sample = s.step(res, t, sample, noise)
+    assert abs(sample.abs().sum().item() - exp_sum) < 1e-2
+    assert abs(sample.abs().mean().item() - exp_mean) < 1e-3
+
+
+def test_ddpm_variance_constants():
+    s = osched.OracleDDPM(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear")
+    assert abs(float(s._get_variance(0)) - 0.0) < 1e-5
+    assert abs(float(s._get_variance(487)) - 0.00979) < 1e-5
+    assert abs(float(s._get_variance(999)) - 0.02) < 1e-5
+
+
+def test_ddim_offset_grid_and_loops():
+    s = osched.OracleDDIM(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                          steps_offset=1)
+    s.set_timesteps(5)
+    assert torch.equal(s.timesteps, torch.LongTensor([801, 601, 401, 201, 1]))
+    for pred, es, em in (("epsilon", 172.0067, 0.223967), ("v_prediction", 52.5302, 0.0684)):
+        s = osched.OracleDDIM(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                              clip_sample=True, prediction_type=pred)
+        s.set_timesteps(10)
+        x = _dummy_sample_deter()
+        for t in s.timesteps:
+            x = s.step(_dummy_model(x, t), t, x)
+        assert abs(x.abs().sum().item() - es) < 1e-2
+        assert abs(x.abs().mean().item() - em) < 1e-3
+
+
+def test_scheduler_goldens_bit_exact():
+    gd = gold("schedulers.npz")
+    sc = osched.SD21_CONFIG
+    for n in (10, 200):
+        o = osched.OracleDDPM(**sc)
+        o.set_timesteps(n)
+        assert np.array_equal(o.timesteps.numpy(), gd[f"ddpm_timesteps_{n}"])
+        oi = osched.OracleDDIM(**sc)
+        oi.set_timesteps(n)
+        assert np.array_equal(oi.timesteps.numpy(), gd[f"ddim_timesteps_{n}"])
+    assert gd["ddpm_timesteps_200"][0] == 995 and gd["ddpm_timesteps_200"][-1] == 0
+    assert gd["ddim_timesteps_200"][0] == 996 and gd["ddim_timesteps_200"][-1] == 1
+    x0 = torch.from_numpy(gd["x0"])
+    noises = torch.from_numpy(gd["noises"])
+    for pred in ("v_prediction", "epsilon"):
+        o = osched.OracleDDPM(**dict(sc, prediction_type=pred))
+        o.set_timesteps(10)
+        x = x0.clone()
+        for i, t in enumerate(o.timesteps):
+            x = o.step(torch.sin(x * 3.0 + float(t) / 1000), t, x, noises[i])
+        assert np.array_equal(x.numpy(), gd[f"ddpm_loop_{pred}"])
+        oi = osched.OracleDDIM(**dict(sc, prediction_type=pred))
+        oi.set_timesteps(10)
+        x = x0.clone()
+        for t in oi.timesteps:
+            x = oi.step(torch.sin(x * 3.0 + float(t) / 1000), t, x)
+        assert np.array_equal(x.numpy(), gd[f"ddim_loop_{pred}"])
+
+
+def test_tiny_unet_golden():
+    gd = gold("tiny_unet.npz")
+    cfg = synth.TINY_UNET_CONFIG
+    sd = synth.synth_state_dict(synth.unet_param_shapes(cfg), seed=0)
+    out = ounet.unet_forward(sd, cfg, torch.from_numpy(gd["sample"]), torch.tensor(int(gd["t"])),
+                             torch.from_numpy(gd["ehs"]), torch.from_numpy(gd["mask"]))
+    assert np.abs(out.numpy() - gd["out"]).max() < 5e-5
+    out2 = ounet.unet_forward(sd, cfg, torch.from_numpy(gd["sample"]), 7, torch.from_numpy(gd["ehs"]), None)
+    assert np.abs(out2.numpy() - gd["out_nomask_t7"]).max() < 5e-5
+
+
+def test_tiny_vae_vocoder_golden():
+    gd = gold("tiny_vae_vocoder.npz")
+    vsd = synth.synth_state_dict(synth.vae_decoder_param_shapes(), seed=0)
+    mel = ovae.decode_first_stage(vsd, torch.from_numpy(gd["z"]), synth.VAE_CONFIG["scale_factor"])
+    assert np.abs(mel.numpy() - gd["mel"]).max() < 1e-4
+    wav, wi = ohifi.decode_to_waveform(vsd, mel)
+    assert np.abs(wav.numpy() - gd["wave"]).max() < 1e-4
+    assert np.abs(wi.astype(np.int32) - gd["wave_i16"].astype(np.int32)).max() <= 2
+    assert wi.dtype == np.int16 and wi.shape == (1, 5152)  # (32 mel frames -> 5*4*2*2*2*32 + tail)
+
+
+def test_tiny_inference_golden():
+    gd = gold("tiny_inference.npz")
+    cfg = synth.TINY_UNET_CONFIG
+    sd = synth.synth_state_dict(synth.unet_param_shapes(cfg), seed=0)
+    o = osched.OracleDDPM(**osched.SD21_CONFIG)
+    noises = [torch.from_numpy(n) for n in gd["noises"]]
+    lat = opipe.inference(sd, cfg, o, torch.from_numpy(gd["embeds"]), torch.from_numpy(gd["mask"]), 4, 3.0,
+                          torch.from_numpy(gd["lat0"]), noises)
+    assert np.abs(lat.numpy() - gd["latents"]).max() < 2e-4
