@@ -73,14 +73,16 @@ typedef struct {
 typedef struct {
   tng_aview a[TNG_MAX_AVIEWS];
   int32_t n_aviews;
-  const void* b; /* bf16 [Ncols, Ktot] */
+  const void* b; /* bf16 [Ncols, Ktot], row stride ldb elements */
   int64_t Ncols, Ktot;
+  int64_t ldb;         /* 0 = Ktot */
   int32_t W, H, NB; /* output pixel grid */
   tng_kgroup g[TNG_MAX_KGROUPS];
   int32_t n_groups;
   /* epilogue */
   const float* bias;   /* [Ncols] or NULL */
-  const float* rowvec; /* [NB, Ncols] per-image vector or NULL */
+  const float* rowvec; /* [NB, rowvec_ld] per-image vector (first Ncols entries used) or NULL */
+  int64_t rowvec_ld;   /* 0 = Ncols */
   const void* res;     /* [rows, ldr] residual or NULL */
   int32_t res_dtype;   /* TNG_DT_* */
   int64_t ldr;

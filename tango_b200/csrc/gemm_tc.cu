@@ -35,6 +35,7 @@ struct GemmKernelParams {
   // epilogue
   const float* bias;
   const float* rowvec;
+  long long rowvec_ld;
   const void* res;
   int res_bf16;
   long long ldr;
@@ -212,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
             }
           }
           if (p.rowvec) {
-            const float* rv = p.rowvec + static_cast<long long>(img) * p.Ncols + col0;
+            const float* rv = p.rowvec + static_cast<long long>(img) * p.rowvec_ld + col0;
             if (vec) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -402,7 +403,8 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   if (d->n_aviews < 1 || d->n_aviews > TNG_MAX_AVIEWS) return set_error(TNG_EINVAL, "n_aviews=%d", d->n_aviews);
   if (d->n_groups < 1 || d->n_groups > TNG_MAX_KGROUPS) return set_error(TNG_EINVAL, "n_groups=%d", d->n_groups);
   if (d->W <= 0 || d->H <= 0 || d->NB <= 0 || d->Ncols <= 0) return set_error(TNG_EINVAL, "bad output grid");
-  if (d->Ktot % 8 != 0) return set_error(TNG_EINVAL, "Ktot=%lld must be a multiple of 8", (long long)d->Ktot);
+  if ((d->ldb > 0 ? d->ldb : d->Ktot) % 8 != 0)
+    return set_error(TNG_EINVAL, "B row stride must be a multiple of 8 elements (Ktot=%lld ldb=%lld)", (long long)d->Ktot, (long long)d->ldb);
 
   GemmKernelParams p;
   memset(&p, 0, sizeof(p));
@@ -460,7 +462,7 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
     p.g[i] = KGroupDev{g.view, g.a_c0, g.dw, g.dh, g.b_k0, g.nkb};
     p.total_kiters += g.nkb;
   }
-  p.bias = d->bias; p.rowvec = d->rowvec; p.res = d->res; p.res_bf16 = (d->res_dtype == TNG_DT_BF16);
+  p.bias = d->bias; p.rowvec = d->rowvec; p.rowvec_ld = d->rowvec_ld > 0 ? d->rowvec_ld : d->Ncols; p.res = d->res; p.res_bf16 = (d->res_dtype == TNG_DT_BF16);
   p.ldr = d->ldr; p.alpha = d->alpha; p.accumulate = d->accumulate;
   p.out_f32 = d->out_f32; p.ld_f32 = d->ld_f32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d->out_bf16); p.ld_bf16 = d->ld_bf16;
@@ -471,7 +473,7 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   bool vec = true;
   if (d->bias && !al16(d->bias)) vec = false;
-  if (d->rowvec && (!al16(d->rowvec) || d->Ncols % 4)) vec = false;
+  if (d->rowvec && (!al16(d->rowvec) || p.rowvec_ld % 4)) vec = false;
   if (d->res) {
     if (!al16(d->res)) vec = false;
     if (p.res_bf16 ? (d->ldr % 8) : (d->ldr % 4)) vec = false;
@@ -495,7 +497,7 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   CUtensorMap bm;
   {
     uint64_t dims[2] = {(uint64_t)d->Ktot, (uint64_t)d->Ncols};
-    uint64_t strides[1] = {(uint64_t)d->Ktot * 2};
+    uint64_t strides[1] = {(uint64_t)(d->ldb > 0 ? d->ldb : d->Ktot) * 2};
     uint32_t box[2] = {(uint32_t)BK, (uint32_t)bn_tile};
     int rc = encode_tmap_bf16(&bm, d->b, 2, dims, strides, box);
     if (rc) return rc;

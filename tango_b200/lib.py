@@ -44,10 +44,10 @@ class KGroup(C.Structure):
 class GemmDesc(C.Structure):
     _fields_ = [
         ("a", AView * MAX_AVIEWS), ("n_aviews", C.c_int32),
-        ("b", C.c_void_p), ("Ncols", C.c_int64), ("Ktot", C.c_int64),
+        ("b", C.c_void_p), ("Ncols", C.c_int64), ("Ktot", C.c_int64), ("ldb", C.c_int64),
         ("W", C.c_int32), ("H", C.c_int32), ("NB", C.c_int32),
         ("g", KGroup * MAX_KGROUPS), ("n_groups", C.c_int32),
-        ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("res", C.c_void_p), ("res_dtype", C.c_int32),
+        ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int64), ("res", C.c_void_p), ("res_dtype", C.c_int32),
         ("ldr", C.c_int64), ("alpha", C.c_float), ("accumulate", C.c_int32),
         ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int64),
         ("act", C.c_int32), ("act_param", C.c_float), ("split_off", C.c_int32), ("block_n", C.c_int32),
@@ -163,12 +163,13 @@ class View:
 def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tensor, W: int, H: int, NB: int, *,
               bias=None, rowvec=None, res=None, alpha: float = 1.0, accumulate: bool = False, out_f32=None,
               out_bf16=None, act: int = ACT_NONE, act_param: float = 0.0, split_off: int = 0, block_n: int = 0,
-              ld_f32: Optional[int] = None, ld_bf16: Optional[int] = None, ldr: Optional[int] = None) -> None:
+              ld_f32: Optional[int] = None, ld_bf16: Optional[int] = None, ldr: Optional[int] = None,
+              rowvec_ld: int = 0) -> None:
     """Launch tng_conv_gemm. groups: (view, a_c0, dw, dh, b_k0, nkb). weight: bf16 [Ncols, Ktot]."""
     lib = load()
     d = GemmDesc()
     require_cuda(weight, bias, rowvec, res, out_f32, out_bf16)
-    assert weight.dtype == torch.bfloat16 and weight.is_contiguous()
+    assert weight.dtype == torch.bfloat16 and weight.stride(1) == 1
     d.n_aviews = len(views)
     for i, v in enumerate(views):
         require_cuda(v.t)
@@ -176,6 +177,7 @@ def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tens
         d.a[i] = AView(v.t.data_ptr() + 2 * v.off, v.C, v.W, v.H, v.NB, v.s_w, v.s_h, v.s_n)
     d.b = weight.data_ptr()
     d.Ncols, d.Ktot = weight.shape
+    d.ldb = weight.stride(0)
     d.W, d.H, d.NB = W, H, NB
     d.n_groups = len(groups)
     if len(groups) > MAX_KGROUPS:
@@ -184,18 +186,19 @@ def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tens
         d.g[i] = KGroup(*g)
     d.bias = ptr(bias)
     d.rowvec = ptr(rowvec)
+    d.rowvec_ld = rowvec_ld
     d.res = ptr(res)
     if res is not None:
         d.res_dtype = _dt(res)
-        d.ldr = res.shape[-1] if ldr is None else ldr
+        d.ldr = res.stride(0) if ldr is None else ldr
     d.alpha = alpha
     d.accumulate = int(accumulate)
     d.out_f32 = ptr(out_f32)
     if out_f32 is not None:
-        d.ld_f32 = out_f32.shape[-1] if ld_f32 is None else ld_f32
+        d.ld_f32 = out_f32.stride(0) if ld_f32 is None else ld_f32
     d.out_bf16 = ptr(out_bf16)
     if out_bf16 is not None:
-        d.ld_bf16 = out_bf16.shape[-1] if ld_bf16 is None else ld_bf16
+        d.ld_bf16 = out_bf16.stride(0) if ld_bf16 is None else ld_bf16
     d.act, d.act_param, d.split_off, d.block_n = act, act_param, split_off, block_n
     check(lib.tng_conv_gemm(C.byref(d), stream_ptr()), "tng_conv_gemm")
 
@@ -205,11 +208,11 @@ def attention(q, k, v, out, *, batch, heads, Lq, Lk, scale, q_col0=0, k_col0=0, 
     lib = load()
     require_cuda(q, k, v, out, kbias)
     d = AttnDesc()
-    d.q, d.ld_q, d.q_col0, d.q_lo_off = q.data_ptr(), q.shape[-1], q_col0, q_lo_off
-    d.k, d.ld_k, d.k_col0, d.k_lo_off = k.data_ptr(), k.shape[-1], k_col0, k_lo_off
-    d.v, d.ld_v, d.v_col0, d.v_lo_off = v.data_ptr(), v.shape[-1], v_col0, v_lo_off
+    d.q, d.ld_q, d.q_col0, d.q_lo_off = q.data_ptr(), q.stride(0), q_col0, q_lo_off
+    d.k, d.ld_k, d.k_col0, d.k_lo_off = k.data_ptr(), k.stride(0), k_col0, k_lo_off
+    d.v, d.ld_v, d.v_col0, d.v_lo_off = v.data_ptr(), v.stride(0), v_col0, v_lo_off
     d.kbias = ptr(kbias)
-    d.out, d.ld_o, d.split_off = out.data_ptr(), out.shape[-1], split_off
+    d.out, d.ld_o, d.split_off = out.data_ptr(), out.stride(0), split_off
     d.batch, d.heads, d.Lq, d.Lk, d.scale, d.nsplit = batch, heads, Lq, Lk, scale, nsplit
     check(lib.tng_attention(C.byref(d), stream_ptr()), "tng_attention")
 
@@ -226,43 +229,43 @@ def groupnorm(x0, x1, NB, HW, groups, stats, gamma, beta, eps, act, y, *, split_
                                   groups, stats.data_ptr(), s), "tng_groupnorm_stats")
     check(lib.tng_groupnorm_apply(x0.data_ptr(), _dt(x0), C0, ptr(x1), 0 if x1 is None else _dt(x1), C1, NB, HW,
                                   groups, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, act,
-                                  y.data_ptr(), y.shape[-1], split_off, ptr(raw),
-                                  0 if raw is None else raw.shape[-1], raw_split_off, s), "tng_groupnorm_apply")
+                                  y.data_ptr(), y.stride(0), split_off, ptr(raw),
+                                  0 if raw is None else raw.stride(0), raw_split_off, s), "tng_groupnorm_apply")
 
 
 def layernorm(x, gamma, beta, eps, y, *, split_off=0):
     require_cuda(x, gamma, beta, y)
     rows, Cc = x.shape
     check(load().tng_layernorm(x.data_ptr(), rows, Cc, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(),
-                               y.shape[-1], split_off, stream_ptr()), "tng_layernorm")
+                               y.stride(0), split_off, stream_ptr()), "tng_layernorm")
 
 
 def cast_act(x, NB, H, W, y, *, Cc=None, upsample2x=False, act=ACT_NONE, act_param=0.0, split_off=0):
     require_cuda(x, y)
     Cc = x.shape[-1] if Cc is None else Cc
-    check(load().tng_cast_act(x.data_ptr(), NB, H, W, Cc, x.shape[-1], int(upsample2x), act, act_param, y.data_ptr(),
-                              y.shape[-1], split_off, stream_ptr()), "tng_cast_act")
+    check(load().tng_cast_act(x.data_ptr(), NB, H, W, Cc, x.stride(0), int(upsample2x), act, act_param, y.data_ptr(),
+                              y.stride(0), split_off, stream_ptr()), "tng_cast_act")
 
 
 def softmax_rows(x, scale, y, *, L=None, split_off=0):
     require_cuda(x, y)
     rows = x.shape[0]
     L = x.shape[1] if L is None else L
-    check(load().tng_softmax_rows(x.data_ptr(), rows, L, x.shape[-1], scale, y.data_ptr(), y.shape[-1], split_off,
+    check(load().tng_softmax_rows(x.data_ptr(), rows, L, x.stride(0), scale, y.data_ptr(), y.stride(0), split_off,
                                   stream_ptr()), "tng_softmax_rows")
 
 
 def transpose_bf16(x, B, R, Cc, y):
     require_cuda(x, y)
-    check(load().tng_transpose_bf16(x.data_ptr(), B, R, Cc, x.shape[-1], y.data_ptr(), y.shape[-1], stream_ptr()),
+    check(load().tng_transpose_bf16(x.data_ptr(), B, R, Cc, x.stride(0), y.data_ptr(), y.stride(0), stream_ptr()),
           "tng_transpose_bf16")
 
 
 def sched_step(model_out, cfg, guidance, sample, noise, coef, prev, next_in, *, B, Cc, HW, split_off=0):
     require_cuda(model_out, sample, noise, coef, prev, next_in)
-    check(load().tng_sched_step(ptr(model_out), 0 if model_out is None else model_out.shape[-1], int(cfg), guidance,
+    check(load().tng_sched_step(ptr(model_out), 0 if model_out is None else model_out.stride(0), int(cfg), guidance,
                                 sample.data_ptr(), ptr(noise), coef.data_ptr(), ptr(prev), ptr(next_in),
-                                0 if next_in is None else next_in.shape[-1], split_off, B, Cc, HW, stream_ptr()),
+                                0 if next_in is None else next_in.stride(0), split_off, B, Cc, HW, stream_ptr()),
           "tng_sched_step")
 
 

@@ -133,7 +133,7 @@ def act_views(x: torch.Tensor, NB: int, H: int, W: int, cin: int, split: bool) -
     """Views for a bf16 operand [rows, cin] (or [rows, 2*cin] = [hi|lo] in split mode).
 
     Returns [view] or, when split and cin is not a multiple of 64, [hi_view, lo_view]."""
-    ld = x.shape[-1]
+    ld = x.stride(0)
     s_w, s_h, s_n = ld, W * ld, H * W * ld
     if not split:
         return [L.View(x, cin, W, H, NB, s_w, s_h, s_n)]
@@ -144,7 +144,7 @@ def act_views(x: torch.Tensor, NB: int, H: int, W: int, cin: int, split: bool) -
 
 def parity_views(x: torch.Tensor, NB: int, H: int, W: int, cin: int, split: bool) -> List[L.View]:
     """Four strided views (ph, pw) of a channels-last tensor for a stride-2 conv (cin % 64 == 0 in split mode)."""
-    ld = x.shape[-1]
+    ld = x.stride(0)
     C_ = 2 * cin if split else cin
     out = []
     for ph in range(2):
@@ -156,7 +156,7 @@ def parity_views(x: torch.Tensor, NB: int, H: int, W: int, cin: int, split: bool
 
 def run_conv(pc: PackedConv, x: torch.Tensor, NB: int, H: int, W: int, *, sc_x: Optional[torch.Tensor] = None,
              rowvec=None, res=None, alpha: float = 1.0, accumulate: bool = False, out_f32=None, out_bf16=None,
-             act: int = L.ACT_NONE, act_param: float = 0.0, block_n: int = 0) -> None:
+             act: int = L.ACT_NONE, act_param: float = 0.0, block_n: int = 0, rowvec_ld: int = 0) -> None:
     """Convolution / linear of the bf16 operand x ([rows, cin] or [hi|lo]) on the (NB, H, W) grid.
 
     For stride 2 (H, W) is the *input* grid; the output grid is (H/2, W/2)."""
@@ -185,7 +185,7 @@ def run_conv(pc: PackedConv, x: torch.Tensor, NB: int, H: int, W: int, *, sc_x: 
         act, block_n = L.ACT_GEGLU, pc.geglu_bn
     L.conv_gemm(views, groups, pc.weight, Wo, Ho, NB, bias=pc.bias, rowvec=rowvec, res=res, alpha=alpha,
                 accumulate=accumulate, out_f32=out_f32, out_bf16=out_bf16, act=act, act_param=act_param,
-                split_off=so, block_n=block_n)
+                split_off=so, block_n=block_n, rowvec_ld=rowvec_ld)
 
 
 def run_linear(pc: PackedConv, x: torch.Tensor, **kw) -> None:

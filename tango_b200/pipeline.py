@@ -1,0 +1,338 @@
+"""AudioDiffusion.inference and the Tango façade on the B200 kernels.
+
+Mirrors /root/reference/models.py:210-305 (`AudioDiffusion.inference`, `prepare_latents`,
+`encode_text_classifier_free`) and /root/reference/tango.py:9-64 (`Tango.generate`, `generate_for_batch`, `chunks`):
+same names, argument meaning, defaults and return types. What changes underneath:
+
+  * the whole UNet forward is one CUDA-graph replay of hand-written sm_100a kernels (tango_b200/unet.py);
+  * cross-attention K/V and the time-embedding projections are computed once per call, not once per step;
+  * CFG combine + scheduler update + re-packing of the next UNet input are ONE kernel (tng_sched_step) fed from a
+    per-step coefficient table, so there is no host sync inside the loop (the reference has two per step);
+  * a prompt batch can be sharded over the GPUs of one box (tango_b200/parallel.py) — samples are independent.
+
+Text encoding (FLAN-T5) is the boundary input of the accelerated path: a Hugging Face T5 encoder
+is used when its weights are available locally; tests and the benchmark inject synthetic `prompt_embeds`.
+"""
+from __future__ import annotations
+
+import json
+import os
+import zlib
+from types import SimpleNamespace
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib as L
+from . import parallel
+from . import synth
+from .schedulers import DDIMScheduler, DDPMScheduler
+from .unet import UNet2DConditionModel
+from .vae import AutoencoderKL
+
+LATENT_HW = (256, 16)  # models.py:259-260 (10.24 s); `latent_shape` may override (30 s clips: (768, 16))
+
+
+class SyntheticTextEncoder:
+    """Deterministic stand-in for FLAN-T5 when no checkpoint is reachable: embeddings are a seeded function of the
+    prompt string (dense Gaussian, like T5 states), padded to the longest prompt of the batch with a proper mask."""
+
+    synthetic = True
+
+    def __init__(self, dim: int, tokens: int = 64):
+        self.dim, self.tokens = dim, tokens
+
+    def encode(self, prompts: Sequence[str], fixed_len: Optional[int] = None):
+        lens = [min(self.tokens, max(1, len(p.split()) + 1)) if p else 1 for p in prompts]
+        Lmax = fixed_len or (max(lens) if any(prompts) else 1)
+        emb = torch.zeros(len(prompts), Lmax, self.dim)
+        mask = torch.zeros(len(prompts), Lmax, dtype=torch.long)
+        for i, p in enumerate(prompts):
+            g = torch.Generator().manual_seed(zlib.crc32(p.encode()) & 0x7FFFFFFF)
+            n = min(lens[i], Lmax)
+            emb[i] = torch.randn(Lmax, self.dim, generator=g)
+            mask[i, :n] = 1
+        return emb, mask
+
+
+class AudioDiffusion:
+    """Inference half of /root/reference/models.py:AudioDiffusion (the training half, :105-208, is out of scope)."""
+
+    def __init__(self, text_encoder_name=None, scheduler_name=None, unet_model_name=None,
+                 unet_model_config_path=None, snr_gamma=None, freeze_text_encoder=True, uncondition=False,
+                 unet_config: Optional[dict] = None, precision: str = "bf16", use_cuda_graph: bool = True):
+        assert unet_model_config_path is not None or unet_config is not None or unet_model_name is not None, \
+            "Either UNet pretrain model name or a config file path is required"
+        if unet_model_name is not None and unet_config is None and unet_model_config_path is None:
+            raise NotImplementedError("set_from='pre-trained' (Stable-Diffusion UNet + group_in/out) is an ablation of the"
+                                      " reference (models.py:88-93) and not on the accelerated path")
+        self.text_encoder_name, self.scheduler_name = text_encoder_name, scheduler_name
+        self.unet_model_config_path, self.snr_gamma = unet_model_config_path, snr_gamma
+        self.freeze_text_encoder, self.uncondition = freeze_text_encoder, uncondition
+        cfg = unet_config if unet_config is not None else UNet2DConditionModel.load_config(unet_model_config_path)
+        self.unet = UNet2DConditionModel.from_config(cfg, precision=precision)
+        self.set_from = "random"
+        self.precision = precision
+        self.use_cuda_graph = use_cuda_graph
+        self.noise_scheduler = DDPMScheduler.from_pretrained(scheduler_name, subfolder="scheduler")
+        self.inference_scheduler = DDPMScheduler.from_pretrained(scheduler_name, subfolder="scheduler")
+        self.device = torch.device("cpu")
+        self.tokenizer = None
+        self.text_encoder = None
+        self._graph = None
+        self._graph_key = None
+        self.last_step_ms: Optional[float] = None
+
+    # ------------------------------------------------------------------------------------------ module plumbing
+    def to(self, device):
+        self.device = torch.device(device)
+        self.unet.to(self.device)
+        if self.text_encoder is not None and hasattr(self.text_encoder, "to"):
+            self.text_encoder.to(self.device)
+        return self
+
+    def eval(self):
+        return self
+
+    def load_state_dict(self, sd, strict: bool = True):
+        """pytorch_model_main.bin holds `unet.*` and `text_encoder.*` keys (tango.py:28)."""
+        unet_sd = {k[len("unet."):]: v for k, v in sd.items() if k.startswith("unet.")}
+        self.unet.load_state_dict(unet_sd, strict=strict)
+        te = {k[len("text_encoder."):]: v for k, v in sd.items() if k.startswith("text_encoder.")}
+        if te and self.text_encoder is not None and not getattr(self.text_encoder, "synthetic", False):
+            self.text_encoder.load_state_dict(te, strict=strict)
+        return SimpleNamespace(missing_keys=[], unexpected_keys=[])
+
+    def _ensure_text_encoder(self):
+        if self.text_encoder is not None:
+            return
+        name = self.text_encoder_name or ""
+        try:
+            from transformers import AutoTokenizer, T5EncoderModel
+            self.tokenizer = AutoTokenizer.from_pretrained(name, local_files_only=True)
+            self.text_encoder = T5EncoderModel.from_pretrained(name, local_files_only=True).to(self.device).eval()
+        except Exception:
+            # offline and no local checkpoint: synthetic conditioning of the right shape (flagged `.synthetic`)
+            self.text_encoder = SyntheticTextEncoder(self.unet.config["cross_attention_dim"])
+
+    # ------------------------------------------------------------------------------------------ text (boundary input)
+    def encode_text(self, prompt: List[str]):
+        """models.py:129-147."""
+        self._ensure_text_encoder()
+        if getattr(self.text_encoder, "synthetic", False):
+            emb, mask = self.text_encoder.encode(prompt)
+            return emb.to(self.device), (mask == 1).to(self.device)
+        batch = self.tokenizer(prompt, max_length=self.tokenizer.model_max_length, padding=True, truncation=True,
+                               return_tensors="pt")
+        ids, am = batch.input_ids.to(self.device), batch.attention_mask.to(self.device)
+        with torch.no_grad():
+            hs = self.text_encoder(input_ids=ids, attention_mask=am)[0]
+        return hs, (am == 1).to(self.device)
+
+    def encode_text_classifier_free(self, prompt: List[str], num_samples_per_prompt: int):
+        """models.py:266-305: returns ([uncond; cond] embeddings (2B, L, D), bool mask (2B, L))."""
+        self._ensure_text_encoder()
+        if getattr(self.text_encoder, "synthetic", False):
+            emb, am = self.text_encoder.encode(prompt)
+            nemb, nam = self.text_encoder.encode([""] * len(prompt), fixed_len=emb.shape[1])
+        else:
+            batch = self.tokenizer(prompt, max_length=self.tokenizer.model_max_length, padding=True, truncation=True,
+                                   return_tensors="pt")
+            ids, am = batch.input_ids.to(self.device), batch.attention_mask.to(self.device)
+            with torch.no_grad():
+                emb = self.text_encoder(input_ids=ids, attention_mask=am)[0]
+            ub = self.tokenizer([""] * len(prompt), max_length=emb.shape[1], padding="max_length", truncation=True,
+                                return_tensors="pt")
+            uids, nam = ub.input_ids.to(self.device), ub.attention_mask.to(self.device)
+            with torch.no_grad():
+                nemb = self.text_encoder(input_ids=uids, attention_mask=nam)[0]
+        emb = emb.repeat_interleave(num_samples_per_prompt, 0)
+        am = am.repeat_interleave(num_samples_per_prompt, 0)
+        nemb = nemb.repeat_interleave(num_samples_per_prompt, 0)
+        nam = nam.repeat_interleave(num_samples_per_prompt, 0)
+        pe = torch.cat([nemb, emb]).to(self.device)
+        pm = torch.cat([nam, am]).to(self.device)
+        return pe, (pm == 1)
+
+    def prepare_latents(self, batch_size, inference_scheduler, num_channels_latents, dtype, device, generator=None,
+                        latent_shape=LATENT_HW):
+        """models.py:259-264."""
+        shape = (batch_size, num_channels_latents, *latent_shape)
+        latents = torch.randn(shape, generator=generator, device=device, dtype=dtype)
+        return latents * inference_scheduler.init_noise_sigma
+
+    # ------------------------------------------------------------------------------------------ the hot loop
+    @torch.no_grad()
+    def inference(self, prompt, inference_scheduler, num_steps=20, guidance_scale=3, num_samples_per_prompt=1,
+                  disable_progress=True, *, prompt_embeds: Optional[torch.Tensor] = None,
+                  boolean_prompt_mask: Optional[torch.Tensor] = None, latents: Optional[torch.Tensor] = None,
+                  noises: Optional[Sequence[torch.Tensor]] = None, generator=None, latent_shape=LATENT_HW,
+                  trace: Optional[list] = None) -> torch.Tensor:
+        """models.py:210-257. Extra keyword-only arguments (all optional): inject conditioning (`prompt_embeds`
+        [(2)B, L, D] + `boolean_prompt_mask`), initial `latents`, per-step `noises` (one (B,8,H,W) tensor per step,
+        used where the reference draws randn) or a torch `generator`; `latent_shape` for clips other than 10 s."""
+        device = self.device
+        if device.type != "cuda":
+            raise L.TangoB200Error("AudioDiffusion.inference runs on CUDA only (there is no CPU fallback)")
+        cfg_on = guidance_scale > 1.0
+        if prompt_embeds is None:
+            if cfg_on:
+                prompt_embeds, boolean_prompt_mask = self.encode_text_classifier_free(prompt, num_samples_per_prompt)
+            else:
+                prompt_embeds, boolean_prompt_mask = self.encode_text(prompt)
+                prompt_embeds = prompt_embeds.repeat_interleave(num_samples_per_prompt, 0)
+                boolean_prompt_mask = boolean_prompt_mask.repeat_interleave(num_samples_per_prompt, 0)
+        Bu = prompt_embeds.shape[0]
+        batch_size = Bu // 2 if cfg_on else Bu
+        sch = inference_scheduler
+        sch.set_timesteps(num_steps, device=device)
+        timesteps = sch.timesteps
+        Cl = self.unet.config["in_channels"]
+        H, W = latent_shape
+        if latents is None:
+            latents = self.prepare_latents(batch_size, sch, Cl, torch.float32, device, generator, latent_shape)
+        else:
+            latents = latents.to(device, torch.float32) * sch.init_noise_sigma
+        sample = latents.contiguous().clone()
+
+        unet = self.unet
+        unet.set_conditioning(prompt_embeds, boolean_prompt_mask)
+        temb_table = unet.time_embedding_table(timesteps)            # [steps, temb_total]
+        coef = sch.coefficient_table(device)                          # [steps, 10]
+        s = unet.s
+        HW = H * W
+        x_in = torch.zeros(Bu * HW, Cl * s, device=device, dtype=torch.bfloat16)
+        model_out = torch.zeros(Bu * HW, unet.config["out_channels"], device=device, dtype=torch.float32)
+        temb_cur = torch.zeros(Bu, temb_table.shape[1], device=device, dtype=torch.float32)
+        ident = torch.tensor([0, 0, 0, 1, 0, 0, 0, 0, 0, 1], device=device, dtype=torch.float32)
+        so = Cl if unet.split else 0
+        # pack the initial latents into the (CFG-duplicated) channels-last bf16 UNet input
+        L.sched_step(None, cfg_on, float(guidance_scale), sample, None, ident, None, x_in, B=batch_size, Cc=Cl, HW=HW,
+                     split_off=so)
+
+        def run_unet():
+            unet.forward_rows(x_in, Bu, H, W, temb_cur, temb_cur.shape[1], out=model_out)
+
+        graph = None
+        if self.use_cuda_graph:
+            key = (Bu, H, W, prompt_embeds.shape[1], id(unet._cond))
+            temb_cur.copy_(temb_table[0:1].expand_as(temb_cur))
+            run_unet()  # warm-up: allocates every scratch buffer, sets kernel attributes
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run_unet()
+            self._graph_key = key
+
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(len(timesteps)):
+            temb_cur.copy_(temb_table[i:i + 1].expand_as(temb_cur))
+            if graph is not None:
+                graph.replay()
+            else:
+                run_unet()
+            noise = None
+            if sch._needs_noise(sch.timestep_at(i)):
+                if noises is not None:
+                    noise = noises[i].to(device, torch.float32).contiguous()
+                else:
+                    noise = torch.randn((batch_size, Cl, H, W), generator=generator, device=device, dtype=torch.float32)
+            L.sched_step(model_out, cfg_on, float(guidance_scale), sample, noise, coef[i], sample, x_in, B=batch_size,
+                         Cc=Cl, HW=HW, split_off=so)
+            if trace is not None:
+                trace.append(sample.clone())
+        ev1.record()
+        torch.cuda.synchronize()
+        self.last_step_ms = ev0.elapsed_time(ev1) / max(1, len(timesteps))
+        return sample
+
+
+class Tango:
+    """tango.py:9-64. `name` is a local directory with the reference's checkpoint layout (vae_config.json,
+    stft_config.json, main_config.json, pytorch_model_{vae,stft,main}.bin); the hub download of the reference needs
+    network access and is replaced by that local path. `Tango.from_synthetic()` builds a random-weight instance."""
+
+    def __init__(self, name="declare-lab/tango", device="cuda:0", precision: str = "bf16", unet_config_path=None):
+        path = name
+        if not os.path.isdir(path):
+            raise FileNotFoundError(
+                f"'{name}' is not a local checkpoint directory. The reference downloads it from the Hugging Face hub "
+                "(tango.py:12); offline, pass the directory of a downloaded snapshot or use Tango.from_synthetic().")
+        vae_config = json.load(open(f"{path}/vae_config.json"))
+        main_config = json.load(open(f"{path}/main_config.json"))
+        if unet_config_path is not None:
+            main_config["unet_model_config_path"] = unet_config_path
+        self._init_modules(vae_config, main_config, device, precision)
+        self.vae.load_state_dict(torch.load(f"{path}/pytorch_model_vae.bin", map_location="cpu"))
+        self.model.load_state_dict(torch.load(f"{path}/pytorch_model_main.bin", map_location="cpu"))
+        print("Successfully loaded checkpoint from:", name)
+
+    def _init_modules(self, vae_config, main_config, device, precision, unet_config=None):
+        self.device = torch.device(device)
+        self.vae = AutoencoderKL(**vae_config, precision=precision).to(device)
+        self.stft = None  # TacotronSTFT is only loaded, never used, at inference (tango.py:19) — "next" row
+        mc = {k: v for k, v in main_config.items()}
+        self.model = AudioDiffusion(**mc, unet_config=unet_config, precision=precision).to(device)
+        self.vae.eval()
+        self.model.eval()
+        self.scheduler = DDPMScheduler.from_pretrained(main_config.get("scheduler_name"), subfolder="scheduler")
+
+    @classmethod
+    def from_synthetic(cls, unet_config: Optional[dict] = None, device="cuda:0", precision: str = "bf16", seed: int = 0,
+                       scheduler: str = "ddpm"):
+        """Random-weight instance with the reference's architecture (no checkpoint is reachable offline)."""
+        self = cls.__new__(cls)
+        ucfg = dict(unet_config or synth.BASE_UNET_CONFIG)
+        self._init_modules(dict(synth.VAE_CONFIG), {"scheduler_name": "stabilityai/stable-diffusion-2-1",
+                                                    "text_encoder_name": None}, device, precision, unet_config=ucfg)
+        self.model.unet.load_state_dict(synth.synth_state_dict(synth.unet_param_shapes(ucfg), seed))
+        self.vae.load_state_dict(synth.synth_state_dict(synth.vae_decoder_param_shapes(), seed))
+        if scheduler == "ddim":
+            self.scheduler = DDIMScheduler.from_pretrained(None)
+        return self
+
+    def chunks(self, lst, n):
+        """ Yield successive n-sized chunks from a list. """
+        for i in range(0, len(lst), n):
+            yield lst[i:i + n]
+
+    def _decode(self, latents: torch.Tensor) -> np.ndarray:
+        """decode_first_stage + decode_to_waveform without leaving channels-last rows (tango.py:47-48)."""
+        B, Cl, H, W = latents.shape
+        rows = latents.float().permute(0, 2, 3, 1).reshape(B * H * W, Cl).contiguous()
+        mel = self.vae.decode_rows(rows, B, H, W)                       # [B*4H*4W, 1] == [B*4H, 64]
+        _, wi = self.vae.vocoder_rows(mel.view(B * 4 * H, 4 * W), B, 4 * H)
+        return wi.cpu().numpy()
+
+    def generate(self, prompt, steps=100, guidance=3, samples=1, disable_progress=True, **kw):
+        """ Genrate audio for a single prompt string. """
+        with torch.no_grad():
+            latents = self.model.inference([prompt], self.scheduler, steps, guidance, samples,
+                                           disable_progress=disable_progress, **kw)
+            wave = self._decode(latents)
+        return wave[0]
+
+    def generate_for_batch(self, prompts, steps=100, guidance=3, samples=1, batch_size=8, disable_progress=True,
+                           shard: bool = False, **kw):
+        """ Genrate audio for a list of prompt strings. With `shard=True` under torch.distributed the prompts are
+        split contiguously over the ranks and rank 0 receives every waveform (other ranks return their own)."""
+        my = list(prompts)
+        lo = 0
+        if shard and parallel.world_size() > 1:
+            lo, hi = parallel.shard_range(len(prompts), parallel.rank(), parallel.world_size())
+            my = list(prompts[lo:hi])
+        outputs = []
+        for k in range(0, len(my), batch_size):
+            batch = my[k: k + batch_size]
+            with torch.no_grad():
+                latents = self.model.inference(batch, self.scheduler, steps, guidance, samples,
+                                               disable_progress=disable_progress, **kw)
+                wave = self._decode(latents)
+                outputs += [item for item in wave]
+        if shard and parallel.world_size() > 1:
+            outputs = parallel.gather_waves(outputs, dst=0)
+        if samples == 1:
+            return outputs
+        return list(self.chunks(outputs, samples))

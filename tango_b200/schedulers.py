@@ -90,12 +90,17 @@ class _SchedulerBase:
     def _finish_set_timesteps(self, device):
         rows = [self._coefficients(int(t)) for t in self.timesteps.tolist()]
         self._coef_host = torch.stack(rows).contiguous()
-        self._t_index = {int(t): i for i, t in enumerate(self.timesteps.tolist())}
+        self._t_list = [int(t) for t in self.timesteps.tolist()]
+        self._t_index = {t: i for i, t in enumerate(self._t_list)}
         self._coef_dev = None
         if device is not None:
             self.timesteps = self.timesteps.to(device)
             if torch.device(device).type == "cuda":
                 self._coef_dev = self._coef_host.to(device)
+
+    def timestep_at(self, i: int) -> int:
+        """Host copy of timesteps[i] (no device sync)."""
+        return self._t_list[i]
 
     def coefficient_table(self, device=None) -> torch.Tensor:
         """[num_steps, 10] fp32 table (row i belongs to timesteps[i])."""

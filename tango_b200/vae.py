@@ -1,0 +1,322 @@
+"""AudioLDM AutoencoderKL *decoder* + HiFi-GAN vocoder on the sm_100a kernels (latents -> mel -> 16 kHz waveform).
+
+Drop-in for the part of /root/reference/audioldm/variational_autoencoder/autoencoder.py that Tango calls
+(`decode_first_stage`, `decode_to_waveform`, `.device()`, `.scale_factor`; tango.py:46-48) with the same
+state_dict layout (`decoder.* post_quant_conv.* vocoder.*`; encoder / quant_conv keys are accepted and ignored —
+they belong to the training path).
+
+decoder:  modules.py:650-683 (conv_in, mid res-attn-res, 3 up levels x 3 ResnetBlocks, nearest x2 + conv, norm_out,
+          swish, conv_out) — same GroupNorm / tcgen05 conv kernels as the UNet. The single-head 512-wide mid
+          AttnBlock (modules.py:204-230) runs as tcgen05 GEMMs  S = q k^T  ->  row softmax  ->  P v  per image.
+vocoder:  hifigan/models.py:149-165 — Conv1d stacks as 1-D implicit GEMMs with leaky-ReLU / residual / 3-way average
+          fused in the epilogues, ConvTranspose1d as GEMM + overlap-add gather, tanh -> int16 in one HBM kernel.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .ops import PackedConv, run_conv, run_linear
+from .synth import HIFIGAN_CONFIG, VAE_CONFIG, vae_decoder_param_shapes
+from .unet import _Buffers
+
+
+class AutoencoderKL:
+    def __init__(self, ddconfig=None, embed_dim=None, scale_factor=1, precision: str = "bf16", **_ignored):
+        self.ddconfig = dict(ddconfig or VAE_CONFIG["ddconfig"])
+        self.embed_dim = embed_dim if embed_dim is not None else VAE_CONFIG["embed_dim"]
+        self.scale_factor = scale_factor
+        assert precision in ("bf16", "split")
+        self.precision, self.split, self.s = precision, precision == "split", 2 if precision == "split" else 1
+        self._device = torch.device("cpu")
+        self._sd: Optional[Dict[str, torch.Tensor]] = None
+        self._packed = False
+        self.hifigan = dict(HIFIGAN_CONFIG)
+
+    # ------------------------------------------------------------------------------------------ reference-style API
+    def device(self):
+        return self._device
+
+    def to(self, device=None, *_a, **_k):
+        if device is not None and not isinstance(device, torch.dtype):
+            device = torch.device(device)
+            if device != self._device:
+                self._device, self._packed = device, False
+        return self
+
+    def eval(self):
+        return self
+
+    def _cfg(self):
+        return {"ddconfig": self.ddconfig, "embed_dim": self.embed_dim}
+
+    def load_state_dict(self, sd, strict: bool = True):
+        want = vae_decoder_param_shapes(self._cfg())
+        missing = [k for k in want if k not in sd]
+        if missing:
+            raise RuntimeError(f"Error(s) in loading state_dict for AutoencoderKL: missing keys {missing[:5]}...")
+        for k, shp in want.items():
+            if tuple(sd[k].shape) != tuple(shp):
+                raise RuntimeError(f"size mismatch for {k}: {tuple(sd[k].shape)} vs {tuple(shp)}")
+        self._sd = {k: sd[k].detach() for k in want}
+        self._packed = False
+        return SimpleNamespace(missing_keys=[], unexpected_keys=[k for k in sd if k not in want])
+
+    # ------------------------------------------------------------------------------------------ packing
+    def _pack(self):
+        if self._packed:
+            return
+        if self._sd is None:
+            raise L.TangoB200Error("AutoencoderKL has no weights: call load_state_dict first")
+        if self._device.type != "cuda":
+            raise L.TangoB200Error("tango_b200 runs on CUDA only: call .to('cuda') (there is no CPU fallback)")
+        L.load()
+        sd, dev, sp = self._sd, self._device, self.split
+        dd = self.ddconfig
+
+        def f32(k):
+            return sd[k].float().contiguous().to(dev)
+
+        def conv(p, **kw):
+            return PackedConv(sd[p + ".weight"], sd.get(p + ".bias"), split=sp, device=dev, **kw)
+
+        def res(p):
+            r = SimpleNamespace()
+            r.n1w, r.n1b, r.n2w, r.n2b = f32(p + ".norm1.weight"), f32(p + ".norm1.bias"), f32(p + ".norm2.weight"), f32(p + ".norm2.bias")
+            r.conv1 = conv(p + ".conv1")
+            if (p + ".nin_shortcut.weight") in sd:
+                r.conv2 = PackedConv(sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], split=sp, device=dev,
+                                     sc_w=sd[p + ".nin_shortcut.weight"], sc_b=sd[p + ".nin_shortcut.bias"])
+            else:
+                r.conv2 = conv(p + ".conv2")
+            r.cin, r.cout = r.conv1.cin, r.conv1.cout
+            return r
+
+        P = SimpleNamespace()
+        # post_quant_conv with the 1/scale_factor of decode_first_stage folded in (autoencoder.py:116-124,60-61)
+        P.pq_w = (sd["post_quant_conv.weight"].float().reshape(sd["post_quant_conv.weight"].shape[0], -1)
+                  * (1.0 / self.scale_factor)).contiguous().to(dev)
+        P.pq_b = f32("post_quant_conv.bias")
+        P.conv_in = conv("decoder.conv_in")
+        P.mid1, P.mid2 = res("decoder.mid.block_1"), res("decoder.mid.block_2")
+        a = "decoder.mid.attn_1"
+        P.attn = SimpleNamespace(nw=f32(a + ".norm.weight"), nb=f32(a + ".norm.bias"))
+        Cc = sd[a + ".q.weight"].shape[0]
+        wq = torch.cat([sd[a + ".q.weight"], sd[a + ".k.weight"], sd[a + ".v.weight"]], 0).reshape(3 * Cc, Cc)
+        bq = torch.cat([sd[a + ".q.bias"], sd[a + ".k.bias"], sd[a + ".v.bias"]], 0)
+        P.attn.qkv = PackedConv(wq, bq, split=sp, device=dev)
+        P.attn.proj = PackedConv(sd[a + ".proj_out.weight"].reshape(Cc, Cc), sd[a + ".proj_out.bias"], split=sp, device=dev)
+        P.attn.C = Cc
+        P.up = []
+        nres = len(dd["ch_mult"])
+        for lvl in reversed(range(nres)):
+            blk = SimpleNamespace(res=[res(f"decoder.up.{lvl}.block.{b}") for b in range(dd["num_res_blocks"] + 1)], up=None)
+            if lvl != 0:
+                blk.up = conv(f"decoder.up.{lvl}.upsample.conv")
+            P.up.append(blk)
+        P.no_w, P.no_b = f32("decoder.norm_out.weight"), f32("decoder.norm_out.bias")
+        P.conv_out = conv("decoder.conv_out")
+
+        # ---- vocoder
+        h = self.hifigan
+        V = SimpleNamespace()
+        V.conv_pre = PackedConv(sd["vocoder.conv_pre.weight"], sd["vocoder.conv_pre.bias"], split=sp, device=dev)
+        V.stages = []
+        nk = len(h["resblock_kernel_sizes"])
+        for i, (u, k) in enumerate(zip(h["upsample_rates"], h["upsample_kernel_sizes"])):
+            st = SimpleNamespace(u=u, k=k, pad=(k - u) // 2)
+            wt = sd[f"vocoder.ups.{i}.weight"]  # (Cin, Cout, k)
+            st.cin, st.cout = wt.shape[0], wt.shape[1]
+            st.up = PackedConv(wt.permute(2, 1, 0).reshape(k * st.cout, st.cin), None, split=sp, device=dev)
+            st.up_bias = f32(f"vocoder.ups.{i}.bias")
+            st.blocks = []
+            for j, rk in enumerate(h["resblock_kernel_sizes"]):
+                rb = SimpleNamespace(c1=[], c2=[])
+                p = f"vocoder.resblocks.{i * nk + j}"
+                for di, d in enumerate(h["resblock_dilation_sizes"][j]):
+                    rb.c1.append(PackedConv(sd[f"{p}.convs1.{di}.weight"], sd[f"{p}.convs1.{di}.bias"], split=sp,
+                                            device=dev, dilation=d))
+                    rb.c2.append(PackedConv(sd[f"{p}.convs2.{di}.weight"], sd[f"{p}.convs2.{di}.bias"], split=sp,
+                                            device=dev, dilation=1))
+                st.blocks.append(rb)
+            V.stages.append(st)
+        V.conv_post = PackedConv(sd["vocoder.conv_post.weight"], sd["vocoder.conv_post.bias"], split=sp, device=dev)
+        self.P, self.V = P, V
+        self._bufs = _Buffers(dev)
+        self._packed = True
+
+    def _buf(self, name, shape, dtype):
+        return self._bufs.get(name, shape, dtype)
+
+    # ------------------------------------------------------------------------------------------ decoder
+    def _resnet(self, name, r, x, NB, H, W):
+        R, s, sp = NB * H * W, self.s, self.split
+        a1 = self._buf("a", (R, r.cin * s), torch.bfloat16)
+        has_sc = r.conv2.cin_sc > 0
+        raw = self._buf("raw", (R, r.cin * s), torch.bfloat16) if has_sc else None
+        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
+        L.groupnorm(x, None, NB, H * W, 32, stats, r.n1w, r.n1b, 1e-6, L.ACT_SILU, a1, split_off=r.cin if sp else 0,
+                    raw=raw, raw_split_off=r.cin if sp else 0)
+        h1 = self._buf("h1", (R, r.cout), torch.float32)
+        run_conv(r.conv1, a1, NB, H, W, out_f32=h1)
+        a2 = self._buf("a", (R, r.cout * s), torch.bfloat16)
+        L.groupnorm(h1, None, NB, H * W, 32, stats, r.n2w, r.n2b, 1e-6, L.ACT_SILU, a2, split_off=r.cout if sp else 0)
+        out = self._buf(name, (R, r.cout), torch.float32)
+        run_conv(r.conv2, a2, NB, H, W, sc_x=raw, res=None if has_sc else x, out_f32=out)
+        return out
+
+    def _attn(self, x, NB, H, W):
+        """modules.py:204-230: softmax(q k^T / sqrt(C)) v over the H*W positions of each image, one head."""
+        t = self.P.attn
+        R, HW, s, sp, Cc = NB * H * W, H * W, self.s, self.split, t.C
+        if HW % 64:
+            raise L.TangoB200Error("VAE attention needs H*W to be a multiple of 64")
+        a = self._buf("a", (R, Cc * s), torch.bfloat16)
+        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
+        L.groupnorm(x, None, NB, HW, 32, stats, t.nw, t.nb, 1e-6, L.ACT_NONE, a, split_off=Cc if sp else 0)
+        qkv = self._buf("vqkv", (R, 3 * Cc * s), torch.bfloat16)  # [q k v | q_lo k_lo v_lo]
+        run_linear(t.qkv, a, out_bf16=qkv)
+        S = self._buf("vS", (HW, HW), torch.float32)
+        Pm = self._buf("vP", (HW, HW * s), torch.bfloat16)
+        vt = self._buf("vVt", (Cc, HW * s), torch.bfloat16)
+        o = self._buf("vo", (R, Cc * s), torch.bfloat16)
+        nkb_c, nkb_hw = Cc // 64, HW // 64
+        lo = 3 * Cc
+        for b in range(NB):
+            rows = qkv[b * HW:(b + 1) * HW]
+            av = L.View(rows, rows.shape[1], HW, 1, 1, rows.stride(0), HW * rows.stride(0), HW * rows.stride(0))
+            # S = q k^T: A columns [0,C) (q), B = the same rows read as a [HW, ld] matrix, columns [C,2C) (k)
+            if sp:
+                g = [(0, 0, 0, 0, Cc, nkb_c), (0, lo, 0, 0, Cc, nkb_c), (0, 0, 0, 0, lo + Cc, nkb_c)]
+            else:
+                g = [(0, 0, 0, 0, Cc, nkb_c)]
+            L.conv_gemm([av], g, rows, HW, 1, 1, out_f32=S)
+            L.softmax_rows(S, float(Cc) ** -0.5, Pm, L=HW, split_off=HW if sp else 0)
+            # V^T (K-major B operand of P v): hi (and lo) halves transposed separately
+            L.transpose_bf16(rows[:, 2 * Cc:3 * Cc], 1, HW, Cc, vt[:, :HW])
+            if sp:
+                L.transpose_bf16(rows[:, lo + 2 * Cc:lo + 3 * Cc], 1, HW, Cc, vt[:, HW:])
+            pv = L.View(Pm, Pm.shape[1], HW, 1, 1, Pm.stride(0), HW * Pm.stride(0), HW * Pm.stride(0))
+            if sp:
+                g = [(0, 0, 0, 0, 0, nkb_hw), (0, HW, 0, 0, 0, nkb_hw), (0, 0, 0, 0, HW, nkb_hw)]
+            else:
+                g = [(0, 0, 0, 0, 0, nkb_hw)]
+            ob = o[b * HW:(b + 1) * HW]
+            L.conv_gemm([pv], g, vt, HW, 1, 1, out_bf16=ob, split_off=Cc if sp else 0)
+        out = self._buf("vattn", (R, Cc), torch.float32)
+        run_linear(t.proj, o, res=x, out_f32=out)
+        return out
+
+    def decode_rows(self, z_rows: torch.Tensor, NB: int, H: int, W: int) -> torch.Tensor:
+        """z_rows fp32 [NB*H*W, 8] (channels-last latents) -> mel fp32 [NB*4H*4W, 1] (== [NB*4H, 64] for W = 16)."""
+        self._pack()
+        P, s, sp = self.P, self.s, self.split
+        R = NB * H * W
+        zc = P.pq_w.shape[0]
+        z1 = self._buf("vz", (R, zc), torch.float32)
+        L.linear_f32(z_rows, P.pq_w, P.pq_b, z1)
+        zb = self._buf("vzb", (R, zc * s), torch.bfloat16)
+        L.cast_act(z1, NB, H, W, zb, split_off=zc if sp else 0)
+        h = self._buf("vconv_in", (R, P.conv_in.cout), torch.float32)
+        run_conv(P.conv_in, zb, NB, H, W, out_f32=h)
+        h = self._resnet("vmid1", P.mid1, h, NB, H, W)
+        h = self._attn(h, NB, H, W)
+        h = self._resnet("vmid2", P.mid2, h, NB, H, W)
+        ch, cw = H, W
+        for li, blk in enumerate(P.up):
+            for bi, r in enumerate(blk.res):
+                h = self._resnet(f"vup{li}_{bi}", r, h, NB, ch, cw)
+            if blk.up is not None:
+                Cc = blk.up.cin
+                xb = self._buf("a", (NB * 4 * ch * cw, Cc * s), torch.bfloat16)
+                L.cast_act(h, NB, ch, cw, xb, upsample2x=True, split_off=Cc if sp else 0)
+                ch, cw = 2 * ch, 2 * cw
+                hu = self._buf(f"vups{li}", (NB * ch * cw, blk.up.cout), torch.float32)
+                run_conv(blk.up, xb, NB, ch, cw, out_f32=hu)
+                h = hu
+        Cc = h.shape[1]
+        a = self._buf("a", (NB * ch * cw, Cc * s), torch.bfloat16)
+        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
+        L.groupnorm(h, None, NB, ch * cw, 32, stats, P.no_w, P.no_b, 1e-6, L.ACT_SILU, a, split_off=Cc if sp else 0)
+        mel = self._buf("vmel", (NB * ch * cw, P.conv_out.cout), torch.float32)
+        run_conv(P.conv_out, a, NB, ch, cw, out_f32=mel)
+        return mel
+
+    def decode_first_stage(self, z: torch.Tensor, predict_cids=False, force_not_quantize=False) -> torch.Tensor:
+        """(B, 8, T/4, 16) latents -> (B, 1, T, 64) log-mel (autoencoder.py:116-124)."""
+        if predict_cids:
+            raise NotImplementedError("predict_cids is not on the Tango path")
+        if not z.is_cuda:
+            raise L.TangoB200Error("decode_first_stage runs on the GPU only (no CPU fallback)")
+        B, Cc, H, W = z.shape
+        rows = z.float().permute(0, 2, 3, 1).reshape(B * H * W, Cc).contiguous()
+        mel = self.decode_rows(rows, B, H, W)
+        oc = mel.shape[1]
+        return mel.view(B, 4 * H, 4 * W, oc).permute(0, 3, 1, 2).contiguous()
+
+    # ------------------------------------------------------------------------------------------ vocoder
+    def vocoder_rows(self, mel_rows: torch.Tensor, B: int, T: int):
+        """mel_rows fp32 [B*T, 64] -> (wave fp32 [B, L], int16 [B, L]) on the device."""
+        self._pack()
+        V, s, sp = self.V, self.s, self.split
+        nm = mel_rows.shape[1]
+        xb = self._buf("hb", (B * T, nm * s), torch.bfloat16)
+        L.cast_act(mel_rows, B, 1, T, xb, split_off=nm if sp else 0)
+        x = self._buf("hx_pre", (B * T, V.conv_pre.cout), torch.float32)
+        run_conv(V.conv_pre, xb, B, 1, T, out_f32=x)
+        Lc = T
+        for si, st in enumerate(V.stages):
+            xb = self._buf("hb", (B * Lc, st.cin * s), torch.bfloat16)
+            L.cast_act(x, B, 1, Lc, xb, act=L.ACT_LRELU, act_param=0.1, split_off=st.cin if sp else 0)
+            Y = self._buf("hY", (B * Lc, st.k * st.cout), torch.float32)
+            run_conv(st.up, xb, B, 1, Lc, out_f32=Y)
+            Lo = (Lc - 1) * st.u - 2 * st.pad + st.k
+            x = self._buf(f"hx{si}", (B * Lo, st.cout), torch.float32)
+            L.convt_gather(Y, B, Lc, st.k, st.cout, st.u, st.pad, Lo, st.up_bias, x)
+            Lc = Lo
+            xs = self._buf(f"hxs{si}", (B * Lc, st.cout), torch.float32)
+            C_ = st.cout
+            so = C_ if sp else 0
+            x_act = self._buf("hxa", (B * Lc, C_ * s), torch.bfloat16)  # lrelu(x): shared first operand of the 3 blocks
+            L.cast_act(x, B, 1, Lc, x_act, act=L.ACT_LRELU, act_param=0.1, split_off=so)
+            nb = len(st.blocks)
+            for j, rb in enumerate(st.blocks):
+                cur, cur_act = x, x_act
+                rbuf = self._buf("hrb", (B * Lc, C_), torch.float32)
+                ract = self._buf("hra", (B * Lc, C_ * s), torch.bfloat16)
+                xt = self._buf("hxt", (B * Lc, C_ * s), torch.bfloat16)
+                nd = len(rb.c1)
+                for di in range(nd):
+                    # xt = lrelu(conv1(lrelu(cur)))  (models.py:98-100), kept only as the bf16 operand of conv2
+                    run_conv(rb.c1[di], cur_act, B, 1, Lc, out_bf16=xt, act=L.ACT_LRELU, act_param=0.1)
+                    if di < nd - 1:
+                        # cur = conv2(xt) + cur ; next operand lrelu(cur) comes from the same epilogue
+                        run_conv(rb.c2[di], xt, B, 1, Lc, res=cur, out_f32=rbuf, out_bf16=ract, act=L.ACT_LRELU,
+                                 act_param=0.1)
+                        cur, cur_act = rbuf, ract
+                    else:
+                        # last conv of the block: xs (+)= (conv2(xt) + cur) / num_kernels  (models.py:154-160)
+                        run_conv(rb.c2[di], xt, B, 1, Lc, res=cur, alpha=1.0 / nb, accumulate=j > 0, out_f32=xs)
+            x = xs
+        cin = V.conv_post.cin
+        xb = self._buf("hb", (B * Lc, cin * s), torch.bfloat16)
+        L.cast_act(x, B, 1, Lc, xb, act=L.ACT_LRELU, act_param=0.01, split_off=cin if sp else 0)  # F.leaky_relu default
+        y = self._buf("hpost", (B * Lc, 1), torch.float32)
+        run_conv(V.conv_post, xb, B, 1, Lc, out_f32=y)
+        wf = self._buf("hwave_f", (B, Lc), torch.float32)
+        wi = self._buf("hwave_i", (B, Lc), torch.int16)
+        L.tanh_to_i16(y, B * Lc, 1, wf, wi)
+        return wf, wi
+
+    def decode_to_waveform(self, dec: torch.Tensor) -> np.ndarray:
+        """(B, 1, T, 64) mel -> int16 numpy (B, L) (autoencoder.py:66-69; hifigan/utilities.py:76-86)."""
+        if not dec.is_cuda:
+            raise L.TangoB200Error("decode_to_waveform runs on the GPU only (no CPU fallback)")
+        B, _, T, nm = dec.shape
+        rows = dec.float().reshape(B * T, nm).contiguous()  # squeeze(1).permute(0,2,1) in channels-last = same memory
+        _, wi = self.vocoder_rows(rows, B, T)
+        return wi.cpu().numpy()
