@@ -111,6 +111,44 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     return lib
 
 
+class _Profiler:
+    """Optional per-launch CUDA-event timing (bench.py's roofline leg). Off by default: zero overhead."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []  # (family, algorithmic flops, algorithmic bytes, start event, end event)
+
+    def start(self):
+        self.records = []
+        self.enabled = True
+
+    def stop(self):
+        self.enabled = False
+        torch.cuda.synchronize()
+        out = {}
+        for fam, fl, by, e0, e1 in self.records:
+            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["bytes"] += by
+        self.records = []
+        return out
+
+    def timed(self, family, flops, nbytes, fn):
+        if not self.enabled:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        self.records.append((family, float(flops), float(nbytes), e0, e1))
+        return r
+
+
+PROF = _Profiler()
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().tng_last_error().decode("utf-8", "replace")
@@ -164,8 +202,9 @@ def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tens
               bias=None, rowvec=None, res=None, alpha: float = 1.0, accumulate: bool = False, out_f32=None,
               out_bf16=None, act: int = ACT_NONE, act_param: float = 0.0, split_off: int = 0, block_n: int = 0,
               ld_f32: Optional[int] = None, ld_bf16: Optional[int] = None, ldr: Optional[int] = None,
-              rowvec_ld: int = 0) -> None:
-    """Launch tng_conv_gemm. groups: (view, a_c0, dw, dh, b_k0, nkb). weight: bf16 [Ncols, Ktot]."""
+              rowvec_ld: int = 0, algo_k: Optional[int] = None) -> None:
+    """Launch tng_conv_gemm. groups: (view, a_c0, dw, dh, b_k0, nkb). weight: bf16 [Ncols, Ktot].
+    algo_k: algorithmic reduction length (taps * Cin of the reference op) for the profiler's FLOP count."""
     lib = load()
     d = GemmDesc()
     require_cuda(weight, bias, rowvec, res, out_f32, out_bf16)
@@ -200,6 +239,11 @@ def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tens
     if out_bf16 is not None:
         d.ld_bf16 = out_bf16.stride(0) if ld_bf16 is None else ld_bf16
     d.act, d.act_param, d.split_off, d.block_n = act, act_param, split_off, block_n
+    if PROF.enabled:
+        k_alg = algo_k if algo_k is not None else sum(g[5] for g in groups) * 64
+        flops = 2.0 * W * H * NB * weight.shape[0] * k_alg
+        PROF.timed("gemm_tc", flops, 0, lambda: check(lib.tng_conv_gemm(C.byref(d), stream_ptr()), "tng_conv_gemm"))
+        return
     check(lib.tng_conv_gemm(C.byref(d), stream_ptr()), "tng_conv_gemm")
 
 
@@ -214,7 +258,8 @@ def attention(q, k, v, out, *, batch, heads, Lq, Lk, scale, q_col0=0, k_col0=0, 
     d.kbias = ptr(kbias)
     d.out, d.ld_o, d.split_off = out.data_ptr(), out.stride(0), split_off
     d.batch, d.heads, d.Lq, d.Lk, d.scale, d.nsplit = batch, heads, Lq, Lk, scale, nsplit
-    check(lib.tng_attention(C.byref(d), stream_ptr()), "tng_attention")
+    PROF.timed("attention_tc", 4.0 * batch * heads * Lq * Lk * 64, 0,
+               lambda: check(lib.tng_attention(C.byref(d), stream_ptr()), "tng_attention"))
 
 
 # --------------------------------------------------------------------------------------------------- norms etc.

@@ -185,7 +185,8 @@ def run_conv(pc: PackedConv, x: torch.Tensor, NB: int, H: int, W: int, *, sc_x: 
         act, block_n = L.ACT_GEGLU, pc.geglu_bn
     L.conv_gemm(views, groups, pc.weight, Wo, Ho, NB, bias=pc.bias, rowvec=rowvec, res=res, alpha=alpha,
                 accumulate=accumulate, out_f32=out_f32, out_bf16=out_bf16, act=act, act_param=act_param,
-                split_off=so, block_n=block_n, rowvec_ld=rowvec_ld)
+                split_off=so, block_n=block_n, rowvec_ld=rowvec_ld,
+                algo_k=len(pc.taps) * pc.cin + pc.cin_sc)
 
 
 def run_linear(pc: PackedConv, x: torch.Tensor, **kw) -> None:

@@ -252,23 +252,25 @@ class UNet2DConditionModel:
         """Project the (frozen, step-invariant) text states to K/V for all 16 cross-attention layers once
         (attention_processor.py:279-284) and turn the mask into the additive bias of unet_2d_condition.py:575-579."""
         self._pack()
-        ehs = encoder_hidden_states.to(self.device, torch.float32).contiguous()
+        ehs = encoder_hidden_states.to(self.device, torch.float32, non_blocking=True).contiguous()
         Bu, Lk, D = ehs.shape
         s = self.s
-        eb = torch.empty(Bu * Lk, D * s, device=self.device, dtype=torch.bfloat16)
+        # persistent buffers (same addresses on every call with the same shapes -> a captured CUDA graph stays valid)
+        eb = self._buf("cond_ehs", (Bu * Lk, D * s), torch.bfloat16)
         L.cast_act(ehs.view(Bu * Lk, D), 1, 1, Bu * Lk, eb, split_off=D if self.split else 0)
         kvs = []
-        for t in self.P["transformers"]:
-            kv = torch.empty(Bu * Lk, 2 * t.C * s, device=self.device, dtype=torch.bfloat16)
+        for i, t in enumerate(self.P["transformers"]):
+            kv = self._buf(f"cond_kv{i}", (Bu * Lk, 2 * t.C * s), torch.bfloat16)
             run_linear(t.kv2, eb, out_bf16=kv)
             kvs.append(kv)
         bias = None
         if encoder_attention_mask is not None:
-            m = encoder_attention_mask.to(self.device)
+            m = encoder_attention_mask.to(self.device, non_blocking=True)
+            bias = self._buf("cond_bias", (Bu, Lk), torch.float32)
             if m.dtype is torch.bool:
-                bias = ((1 - m.to(torch.float32)) * -10000.0).contiguous()
+                bias.copy_((1 - m.to(torch.float32)) * -10000.0)
             else:
-                bias = m.to(torch.float32).contiguous()
+                bias.copy_(m.to(torch.float32))
         self._cond = SimpleNamespace(kvs=kvs, bias=bias, Bu=Bu, Lk=Lk)
 
     def _resnet(self, name, r, x0, x1, NB, H, W, temb, temb_ld):
