@@ -1,14 +1,20 @@
 // attention_tc.cu — tcgen05 flash attention for head width 64 (UNet self- and cross-attention), sm_100a.
 //
-// One CTA = 128 query rows of one (batch, head). Per 128-row KV tile:
-//   S = Q K^T      tcgen05.mma 128x128x16 (K-major A and B straight from TMA SWIZZLE_128B tiles), S in TMEM
-//   softmax        each of the 128 threads owns one query row: tcgen05.ld the row, fp32 online softmax
-//                  (scale, additive key bias, key-length mask), P -> bf16 -> swizzled smem
-//   O += P V       tcgen05.mma 128x64x16 with V consumed as an MN-major B operand (no transpose anywhere)
-// S is double-buffered in TMEM so that Q K^T of tile j+1 runs on the tensor core while tile j is in softmax;
-// K/V tiles are NBUF-deep TMA-prefetched. O is accumulated in registers with the usual rescale.
-// NSPLIT = 2 is the parity mode: every operand carries its bf16 rounding residual and each product is
-// evaluated as hi*hi + lo*hi + hi*lo, which restores ~fp32 accuracy on the bf16 tensor cores.
+// One CTA = 128 query rows of one (batch, head); 128 threads, thread r owns query row r (= TMEM lane r).
+// Per 128-key tile j:
+//   S = Q K_j^T    tcgen05.mma 128x128x16, K-major A/B straight from TMA SWIZZLE_128B tiles, fp32 S in TMEM
+//   softmax        pass 1: row max of the raw scores (tcgen05.ld); pass 2: p = exp2(s*scale*log2e - m) -> bf16 ->
+//                  swizzled smem (the A operand of the next MMA); row sum in fp32. The reference max m is only
+//                  advanced when the row max grew by more than 2^8 ("lazy rescale"), so the common tile does no
+//                  correction work at all.
+//   O += P V_j     tcgen05.mma 128x64x16 accumulating IN TMEM (V consumed as an MN-major B operand, no transpose)
+// When the reference max does move, the warp rescales its O rows in place (tcgen05.ld -> scale -> tcgen05.st).
+// Issue order on the tensor pipe is  P V_j , Q K_{j+1}^T  back to back right after the softmax of tile j, so the
+// S-ready barrier of tile j+1 also certifies that P V_j has drained (P smem and O are safe to touch).
+// Resources are sized for TWO CTAs per SM (112 KB smem, 256 TMEM columns): while one CTA is in its softmax the other
+// one's MMAs keep the tensor pipe busy. K/V tiles are double-buffered and TMA-prefetched one tile ahead.
+// NSPLIT = 2 is the parity mode: every operand carries its bf16 rounding residual and each product is evaluated as
+// hi*hi + lo*hi + hi*lo, which restores ~fp32 accuracy on the bf16 tensor cores (1 CTA / SM).
 #include "tng_ptx.cuh"
 #include "tng_internal.h"
 
@@ -18,6 +24,8 @@ constexpr int AT_BM = 128;   // queries per CTA
 constexpr int AT_BN = 128;   // keys per tile
 constexpr int AT_D = 64;     // head width
 constexpr int AT_CHUNK = AT_BM * 64 * 2;  // one [128][64] bf16 swizzled chunk = 16 KB
+constexpr int AT_NBUF = 2;
+constexpr float AT_LAZY = 8.0f;  // rescale only when the row max grew by more than 2^8
 
 struct AttnParams {
   int Lq, Lk, heads;
@@ -31,31 +39,29 @@ struct AttnParams {
 
 template <int NSPLIT>
 struct AttnCfg {
-  static constexpr int NBUF = (NSPLIT == 1) ? 3 : 2;
   static constexpr int Q_BYTES = NSPLIT * AT_CHUNK;
   static constexpr int KV_BYTES = NSPLIT * AT_CHUNK;      // each of K and V per buffer
   static constexpr int P_BYTES = NSPLIT * 2 * AT_CHUNK;   // [128][128] hi (+ lo)
-  static constexpr int SMEM_BYTES = Q_BYTES + NBUF * 2 * KV_BYTES + P_BYTES + 1024 + 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + AT_NBUF * 2 * KV_BYTES + P_BYTES + 128;
+  static constexpr int TMEM_COLS = 256;                   // S: 128, O: 64
 };
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, (NSPLIT == 1) ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                     const __grid_constant__ CUtensorMap vmap, const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<NSPLIT>;
-  constexpr int NBUF = Cfg::NBUF;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::Q_BYTES;                 // [NBUF][KV_BYTES]
-  uint8_t* sV = sK + NBUF * Cfg::KV_BYTES;         // [NBUF][KV_BYTES]
-  uint8_t* sP = sV + NBUF * Cfg::KV_BYTES;         // hi chunks 0,1 then lo chunks 0,1
+  uint8_t* sV = sK + AT_NBUF * Cfg::KV_BYTES;      // [NBUF][KV_BYTES]
+  uint8_t* sP = sV + AT_NBUF * Cfg::KV_BYTES;      // hi chunks 0,1 then lo chunks 0,1
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
   uint64_t* bar_q = bars;             // [1]
   uint64_t* bar_kv = bars + 1;        // [NBUF]
-  uint64_t* bar_s = bars + 1 + NBUF;  // [2]
-  uint64_t* bar_o = bars + 3 + NBUF;  // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + NBUF);
+  uint64_t* bar_s = bars + 1 + AT_NBUF;  // [1]  S_j ready (and P V_{j-1} drained)
+  uint64_t* bar_o = bars + 2 + AT_NBUF;  // [1]  final P V drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + AT_NBUF);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -65,30 +71,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   const int n_tiles = (p.Lk + AT_BN - 1) / AT_BN;
 
   if (tid == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("[tng] attention: dynamic smem base not 1024-byte aligned\n");
+      __trap();
+    }
     tma_prefetch_desc(&qmap);
     tma_prefetch_desc(&kmap);
     tma_prefetch_desc(&vmap);
     mbar_init(bar_q, 1);
-    for (int i = 0; i < NBUF; ++i) mbar_init(&bar_kv[i], 1);
-    mbar_init(&bar_s[0], 1);
-    mbar_init(&bar_s[1], 1);
+    for (int i = 0; i < AT_NBUF; ++i) mbar_init(&bar_kv[i], 1);
+    mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
     __syncwarp();
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_s[2] = {tmem_base, tmem_base + 128};
-  const uint32_t tm_o = tmem_base + 256;
+  const uint32_t tm_s = tmem_base;
+  const uint32_t tm_o = tmem_base + 128;
 
   auto load_kv = [&](int tile) {
-    const int buf = tile % NBUF;
+    const int buf = tile % AT_NBUF;
     mbar_arrive_expect_tx(&bar_kv[buf], 2 * Cfg::KV_BYTES);
     const int kv0 = tile * AT_BN;
 #pragma unroll
@@ -99,11 +108,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
                   kv0, b);
     }
   };
-  // S[sbuf] = Q K_tile^T  (hi*hi [+ lo*hi + hi*lo])
+  // S = Q K_tile^T  (hi*hi [+ lo*hi + hi*lo]); arrives on bar_s when it (and everything issued before) is done
   auto issue_qk = [&](int tile) {
-    const int buf = tile % NBUF;
+    const int buf = tile % AT_NBUF;
     constexpr uint32_t idesc = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
-    const uint32_t d = tm_s[tile & 1];
     const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + buf * Cfg::KV_BYTES);
     constexpr int NT = (NSPLIT == 1) ? 1 : 3;
     const int qsel[3] = {0, 1, 0}, ksel[3] = {0, 0, 1};
@@ -114,20 +122,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       const uint64_t bdesc = umma_desc_sw128(ka + ksel[t] * AT_CHUNK, 16, 1024);
 #pragma unroll
       for (int k = 0; k < AT_D / 16; ++k) {
-        umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+        umma_bf16(tm_s, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
         acc = 1;
       }
     }
-    umma_commit(&bar_s[tile & 1]);
+    umma_commit(bar_s);
   };
-  // O_partial = P V_tile   (A = P K-major chunks, B = V MN-major: 16 keys per MMA = 2 swizzle atoms = 2048 B)
-  auto issue_pv = [&](int tile) {
-    const int buf = tile % NBUF;
+  // O (+)= P V_tile   (A = P K-major chunks, B = V MN-major: 16 keys per MMA = 2 swizzle atoms = 2048 B)
+  auto issue_pv = [&](int tile, uint32_t accumulate) {
+    const int buf = tile % AT_NBUF;
     constexpr uint32_t idesc = umma_idesc_bf16(AT_BM, AT_D, 0, 1);
     const uint32_t pa = smem_u32(sP), va = smem_u32(sV + buf * Cfg::KV_BYTES);
     constexpr int NT = (NSPLIT == 1) ? 1 : 3;
     const int psel[3] = {0, 1, 0}, vsel[3] = {0, 0, 1};
-    uint32_t acc = 0;
+    uint32_t acc = accumulate;
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
 #pragma unroll
@@ -139,7 +147,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
         acc = 1;
       }
     }
-    umma_commit(bar_o);
   };
 
   if (tid == 0) {
@@ -147,7 +154,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
 #pragma unroll
     for (int s = 0; s < NSPLIT; ++s)
       tma_load_3d(sQ + s * AT_CHUNK, &qmap, bar_q, p.q_col0 + s * p.q_lo_off + head * AT_D, q0, b);
-    for (int t = 0; t < NBUF && t < n_tiles; ++t) load_kv(t);
+    for (int t = 0; t < AT_NBUF && t < n_tiles; ++t) load_kv(t);
     mbar_wait(bar_q, 0);
     mbar_wait(&bar_kv[0], 0);
     tc_fence_after();
@@ -156,45 +163,73 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
 
   const int r = tid;  // query row owned by this thread == TMEM lane
   const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-  float o[AT_D];
-#pragma unroll
-  for (int i = 0; i < AT_D; ++i) o[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
+  const uint32_t ts = tm_s + lane_addr;
+  const uint32_t to = tm_o + lane_addr;
+  float m_ref = -INFINITY;  // reference max used in the exponent (log2 domain)
+  float l_run = 0.f;
+  const float sc = p.scale_log2e;
   const float* kb = p.kbias ? p.kbias + static_cast<long long>(b) * p.Lk : nullptr;
   constexpr float LOG2E = 1.4426950408889634f;
+  uint8_t* prow_base = sP + r * 128;
+  const int rsw = r & 7;
 
   for (int j = 0; j < n_tiles; ++j) {
-    if (tid == 0 && j + 1 < n_tiles) {
-      // S[(j+1)&1] was last read in iteration j-1; every thread has passed a __syncthreads since.
-      mbar_wait(&bar_kv[(j + 1) % NBUF], ((j + 1) / NBUF) & 1);
-      tc_fence_after();
-      issue_qk(j + 1);
-    }
     __syncwarp();
-    mbar_wait(&bar_s[j & 1], (j >> 1) & 1);
+    mbar_wait(bar_s, j & 1);   // S_j complete; in-order tensor pipe => P V_{j-1} complete as well
     tc_fence_after();
-    const uint32_t ts = tm_s[j & 1] + lane_addr;
+    // K/V buffer of tile j-1 is free now: prefetch tile j+1 into it (tile j+1 == (j-1) + NBUF)
+    if (tid == 0 && j >= 1 && j + 1 < n_tiles) load_kv(j + 1);
     const int kv0 = j * AT_BN;
-    // ---- pass 1: row maximum
-    float m_new = m_run;
+    const bool tail = (kb != nullptr) || (kv0 + AT_BN > p.Lk);
+    // ---- pass 1: row maximum (log2 domain)
+    float m_tile = -INFINITY;
+    if (!tail) {
 #pragma unroll 1
-    for (int c = 0; c < AT_BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(ts + c, v);
-      tmem_ld_wait();
+      for (int c = 0; c < AT_BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(ts + c, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int kv = kv0 + c + i;
-        float s = __uint_as_float(v[i]) * p.scale_log2e;
-        if (kb && kv < p.Lk) s += kb[kv] * LOG2E;
-        if (kv < p.Lk) m_new = fmaxf(m_new, s);
+        for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
+      }
+      m_tile *= sc;  // scale > 0
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < AT_BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(ts + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kv = kv0 + c + i;
+          if (kv < p.Lk) {
+            float s = __uint_as_float(v[i]) * sc;
+            if (kb) s += kb[kv] * LOG2E;
+            m_tile = fmaxf(m_tile, s);
+          }
+        }
       }
     }
-    const float alpha = exp2f(m_run - m_new);  // 0 on the first tile (m_run = -inf, m_new finite)
-    m_run = m_new;
-    l_run *= alpha;
+    // ---- lazy rescale of the running state (warp-uniform decision; tcgen05.ld/st are warp collectives)
+    const bool need = m_tile > m_ref + AT_LAZY;
+    if (__any_sync(0xffffffffu, need)) {
+      const float m_new = need ? m_tile : m_ref;
+      const float f = (j == 0) ? 0.f : ex2_approx(m_ref - m_new);  // 1 for rows that keep their reference
+      l_run *= f;
+      if (j > 0) {
 #pragma unroll
-    for (int i = 0; i < AT_D; ++i) o[i] *= alpha;
+        for (int c = 0; c < AT_D; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(to + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+          tmem_st32(to + c, v);
+        }
+        tmem_st_wait();
+      }
+      m_ref = m_new;
+    }
     // ---- pass 2: probabilities -> bf16 (hi/lo) -> swizzled smem
 #pragma unroll 1
     for (int c = 0; c < AT_BN; c += 32) {
@@ -202,17 +237,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       tmem_ld32(ts + c, v);
       tmem_ld_wait();
       float pr[32];
+      if (!tail) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int kv = kv0 + c + i;
-        float s = __uint_as_float(v[i]) * p.scale_log2e;
-        if (kb && kv < p.Lk) s += kb[kv] * LOG2E;
-        pr[i] = (kv < p.Lk) ? exp2f(s - m_new) : 0.f;
-        l_run += pr[i];
+        for (int i = 0; i < 32; ++i) {
+          pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -m_ref));
+          l_run += pr[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kv = kv0 + c + i;
+          float s = __uint_as_float(v[i]) * sc;
+          if (kb && kv < p.Lk) s += kb[kv] * LOG2E;
+          pr[i] = (kv < p.Lk) ? ex2_approx(s - m_ref) : 0.f;
+          l_run += pr[i];
+        }
       }
-      const int chunk = c >> 6;              // which 64-key chunk
-      const int u0 = (c & 63) >> 3;          // first 16-byte unit inside the 128-byte row
-      uint8_t* prow = sP + chunk * AT_CHUNK + r * 128;
+      uint8_t* prow = prow_base + (c >> 6) * AT_CHUNK;
+      const int u0 = (c & 63) >> 3;  // first 16-byte unit inside the 128-byte row
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         uint4 w;
@@ -220,7 +262,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
         w.y = pack_bf16(pr[8 * u + 2], pr[8 * u + 3]);
         w.z = pack_bf16(pr[8 * u + 4], pr[8 * u + 5]);
         w.w = pack_bf16(pr[8 * u + 6], pr[8 * u + 7]);
-        *reinterpret_cast<uint4*>(prow + (((u0 + u) ^ (r & 7)) << 4)) = w;
+        *reinterpret_cast<uint4*>(prow + (((u0 + u) ^ rsw) << 4)) = w;
         if (NSPLIT == 2) {
           float lo[8];
 #pragma unroll
@@ -228,63 +270,58 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
           uint4 wl;
           wl.x = pack_bf16(lo[0], lo[1]); wl.y = pack_bf16(lo[2], lo[3]);
           wl.z = pack_bf16(lo[4], lo[5]); wl.w = pack_bf16(lo[6], lo[7]);
-          *reinterpret_cast<uint4*>(prow + 2 * AT_CHUNK + (((u0 + u) ^ (r & 7)) << 4)) = wl;
+          *reinterpret_cast<uint4*>(prow + 2 * AT_CHUNK + (((u0 + u) ^ rsw) << 4)) = wl;
         }
       }
     }
-    // P (generic-proxy writes) must be visible to the tensor core (async proxy); S reads are complete.
+    // P (generic-proxy writes) must be visible to the tensor core (async proxy); all S reads / O rescales are done.
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      issue_pv(j);
-    }
-    __syncwarp();
-    mbar_wait(bar_o, j & 1);
-    tc_fence_after();
-    {
-      const uint32_t to = tm_o + lane_addr;
-#pragma unroll
-      for (int c = 0; c < AT_D; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(to + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(v[i]);
+      issue_pv(j, j > 0 ? 1u : 0u);
+      if (j + 1 < n_tiles) {
+        mbar_wait(&bar_kv[(j + 1) % AT_NBUF], ((j + 1) / AT_NBUF) & 1);
+        tc_fence_after();
+        issue_qk(j + 1);       // commits bar_s after P V_j and Q K_{j+1}^T
+      } else {
+        umma_commit(bar_o);
       }
     }
-    // K/V buffer j%NBUF is free now (Q K^T of tile j and P V of tile j have completed): prefetch tile j+NBUF.
-    if (tid == 0 && j + NBUF < n_tiles) load_kv(j + NBUF);
-    // everyone must have read O_partial before the next P V overwrites it; P smem is rewritten next iteration
-    // only after bar_s, but the O TMEM read needs this barrier.
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
   }
 
   // ---- finalize: O / l -> bf16 (hi/lo)
+  __syncwarp();
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
   const int q = q0 + r;
-  if (q < p.Lq) {
-    const float inv = 1.0f / l_run;
-    __nv_bfloat16* op = p.out + (static_cast<long long>(b) * p.Lq + q) * p.ld_o + head * AT_D;
+  const float inv = 1.0f / l_run;
+  __nv_bfloat16* op = p.out + (static_cast<long long>(b) * p.Lq + q) * p.ld_o + head * AT_D;
 #pragma unroll
-    for (int i = 0; i < AT_D; i += 8) {
-      float y[8];
+  for (int c = 0; c < AT_D; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(to + c, v);
+    tmem_ld_wait();
+    if (q < p.Lq) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) y[t] = o[i + t] * inv;
-      uint4 w;
-      w.x = pack_bf16(y[0], y[1]); w.y = pack_bf16(y[2], y[3]);
-      w.z = pack_bf16(y[4], y[5]); w.w = pack_bf16(y[6], y[7]);
-      *reinterpret_cast<uint4*>(op + i) = w;
-      if (p.split_off > 0) {
-        float lo[8];
+      for (int i = 0; i < 32; i += 8) {
+        float y[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) lo[t] = y[t] - __bfloat162float(__float2bfloat16_rn(y[t]));
-        uint4 wl;
-        wl.x = pack_bf16(lo[0], lo[1]); wl.y = pack_bf16(lo[2], lo[3]);
-        wl.z = pack_bf16(lo[4], lo[5]); wl.w = pack_bf16(lo[6], lo[7]);
-        *reinterpret_cast<uint4*>(op + p.split_off + i) = wl;
+        for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(v[i + t]) * inv;
+        uint4 w;
+        w.x = pack_bf16(y[0], y[1]); w.y = pack_bf16(y[2], y[3]);
+        w.z = pack_bf16(y[4], y[5]); w.w = pack_bf16(y[6], y[7]);
+        *reinterpret_cast<uint4*>(op + c + i) = w;
+        if (p.split_off > 0) {
+          float lo[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) lo[t] = y[t] - __bfloat162float(__float2bfloat16_rn(y[t]));
+          uint4 wl;
+          wl.x = pack_bf16(lo[0], lo[1]); wl.y = pack_bf16(lo[2], lo[3]);
+          wl.z = pack_bf16(lo[4], lo[5]); wl.w = pack_bf16(lo[6], lo[7]);
+          *reinterpret_cast<uint4*>(op + p.split_off + c + i) = wl;
+        }
       }
     }
   }
@@ -292,7 +329,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -321,6 +358,7 @@ extern "C" int tng_attention(const tng_attn_desc* d, void* stream) {
   if (!d || !d->q || !d->k || !d->v || !d->out) return set_error(TNG_EINVAL, "attention: null argument");
   if (d->nsplit != 1 && d->nsplit != 2) return set_error(TNG_EINVAL, "attention: nsplit=%d", d->nsplit);
   if (d->batch <= 0 || d->heads <= 0 || d->Lq <= 0 || d->Lk <= 0) return set_error(TNG_EINVAL, "attention: bad sizes");
+  if (d->scale <= 0.f) return set_error(TNG_EINVAL, "attention: scale must be positive");
   if (d->ld_o % 8 || d->split_off % 8 || (reinterpret_cast<uintptr_t>(d->out) & 15))
     return set_error(TNG_EINVAL, "attention: output must allow 16-byte stores");
   AttnParams p;

@@ -42,42 +42,59 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-constexpr int GN_ROWS = 64;  // pixels per CTA
+// Thread layout: a CTA owns GN_ROWS pixels of one image; thread t keeps a FIXED channel quad q = t % QT and walks the
+// rows r = t / QT, + RL, ... (QT = min(C/4, 256) quad threads, RL = 256 / QT row lanes), so consecutive threads read
+// consecutive 16-byte quads of a row (coalesced) and the per-channel constants live in registers.
+constexpr int GN_ROWS = 128;  // pixels per CTA
 
 __global__ void __launch_bounds__(256) gn_stats_kernel(const void* x0, int dt0, int C0, const void* x1, int dt1, int C1,
                                                         long long HW, int groups, double* stats) {
-  __shared__ double s_sum[64], s_sq[64];
+  __shared__ float s_sum[64], s_sq[64];
   const int n = blockIdx.y;
   const long long r0 = static_cast<long long>(blockIdx.x) * GN_ROWS;
   const int C = C0 + C1;
   const int cpg = C / groups;
-  if (threadIdx.x < groups) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+  const int Q = C / 4;
+  const int QT = Q < 256 ? Q : 256;
+  const int RL = 256 / QT;
+  const int rl = threadIdx.x / QT;
+  if (threadIdx.x < groups) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
   __syncthreads();
   const int nrows = static_cast<int>((HW - r0) < GN_ROWS ? (HW - r0) : GN_ROWS);
-  for (int q = threadIdx.x; q < C / 4; q += blockDim.x) {
-    const int c = q * 4;
-    const bool first = c < C0;
-    const void* base = first ? x0 : x1;
-    const int dt = first ? dt0 : dt1;
-    const int Cs = first ? C0 : C1;
-    const int cc = first ? c : c - C0;
-    float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-    for (int r = 0; r < nrows; ++r) {
-      const float4 v = load4(base, dt, (n * HW + r0 + r) * Cs + cc);
-      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-      ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
-    }
+  if (rl < RL) {
+    for (int q = threadIdx.x - rl * QT; q < Q; q += QT) {
+      const int c = q * 4;
+      const bool first = c < C0;
+      const void* base = first ? x0 : x1;
+      const int dt = first ? dt0 : dt1;
+      const int Cs = first ? C0 : C1;
+      const int cc = first ? c : c - C0;
+      float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+      const long long rbase = n * HW + r0;
+#pragma unroll 4
+      for (int r = rl; r < nrows; r += RL) {
+        const float4 v = load4(base, dt, (rbase + r) * Cs + cc);
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
+      }
+      const int g0 = c / cpg, g3 = (c + 3) / cpg;
+      if (g0 == g3) {
+        atomicAdd(&s_sum[g0], (s[0] + s[1]) + (s[2] + s[3]));
+        atomicAdd(&s_sq[g0], (ss[0] + ss[1]) + (ss[2] + ss[3]));
+      } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int g = (c + j) / cpg;
-      atomicAdd(&s_sum[g], static_cast<double>(s[j]));
-      atomicAdd(&s_sq[g], static_cast<double>(ss[j]));
+        for (int j = 0; j < 4; ++j) {
+          const int g = (c + j) / cpg;
+          atomicAdd(&s_sum[g], s[j]);
+          atomicAdd(&s_sq[g], ss[j]);
+        }
+      }
     }
   }
   __syncthreads();
   if (threadIdx.x < groups) {
-    atomicAdd(&stats[(static_cast<long long>(n) * groups + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
-    atomicAdd(&stats[(static_cast<long long>(n) * groups + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+    atomicAdd(&stats[(static_cast<long long>(n) * groups + threadIdx.x) * 2 + 0], static_cast<double>(s_sum[threadIdx.x]));
+    atomicAdd(&stats[(static_cast<long long>(n) * groups + threadIdx.x) * 2 + 1], static_cast<double>(s_sq[threadIdx.x]));
   }
 }
 
@@ -86,42 +103,58 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, 
                                                         const float* gamma, const float* beta, float eps, int act,
                                                         __nv_bfloat16* y, long long ld_y, int split_off,
                                                         __nv_bfloat16* raw, long long ld_raw, int raw_split_off) {
-  extern __shared__ float s_ab[];  // scale[C], shift[C]
+  __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.y;
   const int C = C0 + C1;
   const int cpg = C / groups;
-  float* s_scale = s_ab;
-  float* s_shift = s_ab + C;
-  const double cnt = static_cast<double>(HW) * cpg;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const double sum = stats[(static_cast<long long>(n) * groups + g) * 2 + 0];
-    const double sq = stats[(static_cast<long long>(n) * groups + g) * 2 + 1];
+  if (threadIdx.x < groups) {
+    const double cnt = static_cast<double>(HW) * cpg;
+    const double sum = stats[(static_cast<long long>(n) * groups + threadIdx.x) * 2 + 0];
+    const double sq = stats[(static_cast<long long>(n) * groups + threadIdx.x) * 2 + 1];
     const double mean = sum / cnt;
     double var = sq / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float sc = rstd * gamma[c];
-    s_scale[c] = sc;
-    s_shift[c] = beta[c] - static_cast<float>(mean) * sc;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   }
   __syncthreads();
   const long long r0 = static_cast<long long>(blockIdx.x) * GN_ROWS;
   const int nrows = static_cast<int>((HW - r0) < GN_ROWS ? (HW - r0) : GN_ROWS);
   const int Q = C / 4;
-  for (int i = threadIdx.x; i < nrows * Q; i += blockDim.x) {
-    const int r = i / Q, q = i - r * Q;
+  const int QT = Q < 256 ? Q : 256;
+  const int RL = 256 / QT;
+  const int rl = threadIdx.x / QT;
+  if (rl >= RL) return;
+  for (int q = threadIdx.x - rl * QT; q < Q; q += QT) {
     const int c = q * 4;
-    const long long row = n * HW + r0 + r;
     const bool first = c < C0;
-    const float4 v = first ? load4(x0, dt0, row * C0 + c) : load4(x1, dt1, row * C1 + (c - C0));
-    float4 o;
-    o.x = act_f(v.x * s_scale[c] + s_shift[c], act, 0.f);
-    o.y = act_f(v.y * s_scale[c + 1] + s_shift[c + 1], act, 0.f);
-    o.z = act_f(v.z * s_scale[c + 2] + s_shift[c + 2], act, 0.f);
-    o.w = act_f(v.w * s_scale[c + 3] + s_shift[c + 3], act, 0.f);
-    store4_split(y + row * ld_y + c, o, split_off);
-    if (raw) store4_split(raw + row * ld_raw + c, v, raw_split_off);
+    const void* base = first ? x0 : x1;
+    const int dt = first ? dt0 : dt1;
+    const int Cs = first ? C0 : C1;
+    const int cc = first ? c : c - C0;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float sc[4], sh[4];
+    const float gm[4] = {g4.x, g4.y, g4.z, g4.w}, bt[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cpg;
+      sc[j] = s_rstd[g] * gm[j];
+      sh[j] = bt[j] - s_mean[g] * sc[j];
+    }
+    const long long rbase = n * HW + r0;
+#pragma unroll 4
+    for (int r = rl; r < nrows; r += RL) {
+      const long long row = rbase + r;
+      const float4 v = load4(base, dt, row * Cs + cc);
+      float4 o;
+      o.x = act_f(v.x * sc[0] + sh[0], act, 0.f);
+      o.y = act_f(v.y * sc[1] + sh[1], act, 0.f);
+      o.z = act_f(v.z * sc[2] + sh[2], act, 0.f);
+      o.w = act_f(v.w * sc[3] + sh[3], act, 0.f);
+      store4_split(y + row * ld_y + c, o, split_off);
+      if (raw) store4_split(raw + row * ld_raw + c, v, raw_split_off);
+    }
   }
 }
 
@@ -410,13 +443,7 @@ extern "C" int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, cons
   if (!x0 || !stats || !y || C % groups || C0 % 4 || (x1 && C1 % 4) || ld_y % 4 || split_off % 4 || C > 8192)
     return set_error(TNG_EINVAL, "groupnorm_apply: bad shape");
   dim3 grid((unsigned)((HW + GN_ROWS - 1) / GN_ROWS), (unsigned)NB);
-  const size_t smem = sizeof(float) * 2 * C;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-    attr = true;
-  }
-  gn_apply_kernel<<<grid, 256, smem, ST(stream)>>>(x0, dt0, (int)C0, x1, dt1, x1 ? (int)C1 : 0, HW, groups, stats, gamma,
+  gn_apply_kernel<<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, x1, dt1, x1 ? (int)C1 : 0, HW, groups, stats, gamma,
                                                     beta, eps, act, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off,
                                                     reinterpret_cast<__nv_bfloat16*>(raw_bf16), ld_raw, raw_split_off);
   count_launch();

@@ -5,19 +5,25 @@
 //   warp 1 (1 thread) : MMA issuer    — tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32 in TMEM), 128 x BN x 16 per
 //                                         instruction, tcgen05.commit releases smem slots / publishes accumulators
 //   warp 2            : TMEM allocator (alloc / dealloc)
-//   warps 4..7        : epilogue      — tcgen05.ld 32x32b, fused bias / per-image vector / residual / scale /
-//                                         activation (SiLU, leaky-ReLU, GEGLU) / bf16 hi-lo split, direct stores
-// Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+//   warps 4..11       : epilogue (8 warps, two per TMEM lane quarter, alternating 32-column chunks) —
+//                       tcgen05.ld 32x32b -> XOR-swizzled smem transpose -> fully coalesced global traffic (8 lanes own
+//                       one 128-byte row segment) with fused bias / per-image vector / residual / scale / accumulate /
+//                       activation (SiLU, leaky-ReLU, GEGLU) / bf16 hi-lo split. Eight warps (two per scheduler) and
+//                       loads-before-use give the epilogue the memory- and instruction-level parallelism it needs to
+//                       stay hidden behind the MMA main loop of the next tile (two TMEM accumulator stages).
 //
 // See include/tango_b200.h (tng_conv_gemm) for the operator contract and the reference call sites it replaces.
 #include "tng_ptx.cuh"
 #include "tng_internal.h"
+#include <stdlib.h>
 
 namespace tng {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements per 128-byte swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int GEMM_THREADS = 384;
+constexpr int EPI_WARPS = 8;
 
 struct KGroupDev {
   int view, a_c0, dw, dh, b_k0, nkb;
@@ -48,18 +54,21 @@ struct GemmKernelParams {
   int act;
   float act_param;
   int split_off;
-  int vec_ok;  // all row strides / bases allow 16-byte vector access
+  int vec_ok;    // all row strides / bases allow 16-byte vector access
+  int fast_epi;  // vec_ok && Ncols % 4 == 0
+  int dbg;       // TNG_GEMM_DBG: 1 = skip epilogue body, 2 = TMEM loads only (profiling experiments)
 };
 
 template <int BN>
 struct GemmCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // per epilogue warp: 32 x 32 fp32 swizzled transpose tile
+  static constexpr int STAGES_RAW = (227 * 1024 - EPI_BYTES - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int ACC_STRIDE = TMEM_COLS / 2;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act, float p) {
@@ -68,19 +77,349 @@ __device__ __forceinline__ float apply_act(float x, int act, float p) {
   return x;
 }
 
+struct EpiRows {
+  long long row[8];
+  int img[8];
+  uint32_t valid;
+};
+
+// One 32-row x 32-column chunk, already staged (swizzled) in `st`: lanes (rsub = lane >> 3, cg = lane & 7) own the
+// 4 columns [4cg, 4cg+4) of rows 4i + rsub, i = 0..7.
+template <bool RES, bool F32, bool BF16, bool VEC>
+__device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const float* st, const EpiRows& R, int rsub, int cg,
+                                          int col) {
+  const bool col_ok = col < p.Ncols;
+  const bool has_res = RES && (p.res != nullptr);
+  const bool has_acc = F32 && (p.accumulate != 0);
+  const bool has_f32 = F32 && (p.out_f32 != nullptr);
+  const bool has_bf = BF16 && (p.out_bf16 != nullptr);
+  // ---- all global loads of the chunk first (independent -> in flight together)
+  float4 rres[8], rold[8];
+  if (has_res) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok && ((R.valid >> i) & 1)) {
+        if (VEC) {
+          if (p.res_bf16) {
+            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + R.row[i] * p.ldr + col);
+            const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            r4 = make_float4(f0.x, f0.y, f1.x, f1.y);
+          } else {
+            r4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + R.row[i] * p.ldr + col);
+          }
+        } else {
+          float t[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int j = 0; j < 4; ++j)
+            if (col + j < p.Ncols)
+              t[j] = p.res_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[R.row[i] * p.ldr + col + j])
+                                : reinterpret_cast<const float*>(p.res)[R.row[i] * p.ldr + col + j];
+          r4 = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+      rres[i] = r4;
+    }
+  }
+  if (has_acc) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok && ((R.valid >> i) & 1)) {
+        if (VEC) {
+          r4 = *reinterpret_cast<const float4*>(p.out_f32 + R.row[i] * p.ld_f32 + col);
+        } else {
+          float t[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int j = 0; j < 4; ++j)
+            if (col + j < p.Ncols) t[j] = p.out_f32[R.row[i] * p.ld_f32 + col + j];
+          r4 = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+      rold[i] = r4;
+    }
+  }
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias && col_ok) {
+    if (VEC) {
+      b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    } else {
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < 4; ++j)
+        if (col + j < p.Ncols) t[j] = __ldg(p.bias + col + j);
+      b4 = make_float4(t[0], t[1], t[2], t[3]);
+    }
+  }
+  const bool has_rv = (p.rowvec != nullptr);
+  const float alpha = p.alpha;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + rsub;
+    float4 a = *reinterpret_cast<const float4*>(st + r * 32 + ((cg ^ (r & 7)) << 2));
+    if (!col_ok || !((R.valid >> i) & 1)) continue;
+    a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+    if (has_rv) {
+      const float* rv = p.rowvec + static_cast<long long>(R.img[i]) * p.rowvec_ld + col;
+      if (VEC) {
+        const float4 r4 = __ldg(reinterpret_cast<const float4*>(rv));
+        a.x += r4.x; a.y += r4.y; a.z += r4.z; a.w += r4.w;
+      } else {
+        if (col + 0 < p.Ncols) a.x += __ldg(rv + 0);
+        if (col + 1 < p.Ncols) a.y += __ldg(rv + 1);
+        if (col + 2 < p.Ncols) a.z += __ldg(rv + 2);
+        if (col + 3 < p.Ncols) a.w += __ldg(rv + 3);
+      }
+    }
+    if (has_res) { a.x += rres[i].x; a.y += rres[i].y; a.z += rres[i].z; a.w += rres[i].w; }
+    a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha;
+    if (has_f32) {
+      if (has_acc) { a.x += rold[i].x; a.y += rold[i].y; a.z += rold[i].z; a.w += rold[i].w; }
+      float* op = p.out_f32 + R.row[i] * p.ld_f32 + col;
+      if (VEC) {
+        *reinterpret_cast<float4*>(op) = a;
+      } else {
+        const float t[4] = {a.x, a.y, a.z, a.w};
+        for (int j = 0; j < 4; ++j)
+          if (col + j < p.Ncols) op[j] = t[j];
+      }
+    }
+    if (has_bf) {
+      __nv_bfloat16* op = p.out_bf16 + R.row[i] * p.ld_bf16 + col;
+      const float y0 = apply_act(a.x, p.act, p.act_param), y1 = apply_act(a.y, p.act, p.act_param);
+      const float y2 = apply_act(a.z, p.act, p.act_param), y3 = apply_act(a.w, p.act, p.act_param);
+      if (VEC) {
+        uint2 u;
+        u.x = pack_bf16(y0, y1); u.y = pack_bf16(y2, y3);
+        *reinterpret_cast<uint2*>(op) = u;
+        if (p.split_off > 0) {
+          uint2 l;
+          l.x = pack_bf16(y0 - __bfloat162float(__float2bfloat16_rn(y0)), y1 - __bfloat162float(__float2bfloat16_rn(y1)));
+          l.y = pack_bf16(y2 - __bfloat162float(__float2bfloat16_rn(y2)), y3 - __bfloat162float(__float2bfloat16_rn(y3)));
+          *reinterpret_cast<uint2*>(op + p.split_off) = l;
+        }
+      } else {
+        const float t[4] = {y0, y1, y2, y3};
+        for (int j = 0; j < 4; ++j) {
+          if (col + j < p.Ncols) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(t[j]);
+            op[j] = hi;
+            if (p.split_off > 0) op[p.split_off + j] = __float2bfloat16_rn(t[j] - __bfloat162float(hi));
+          }
+        }
+      }
+    }
+  }
+}
+
+// Lean path for FULL tiles (all 128 rows valid, all 32 columns of the chunk < Ncols, 16-byte aligned): the rows of a
+// tile are consecutive output rows (the host tiling guarantees it), so slot i of a lane is row r0 + 4i and every
+// pointer advances by a constant stride — a few instructions per 16-byte access, no per-element predicates.
+template <bool RES, bool F32, bool BF16>
+__device__ __forceinline__ void epi_chunk_full(const GemmKernelParams& p, const float* st, long long r0, int img0,
+                                               int rsub, int cg, int col, bool rv_uniform) {
+  float4 add4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) add4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  if (p.rowvec && rv_uniform) {
+    const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(img0) * p.rowvec_ld + col));
+    add4.x += r4.x; add4.y += r4.y; add4.z += r4.z; add4.w += r4.w;
+  }
+  float4 rres[8];
+  if (RES) {
+    if (p.res_bf16) {
+      const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + r0 * p.ldr + col;
+      const long long rs = 4 * p.ldr;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint2 u = *reinterpret_cast<const uint2*>(rp + i * rs);
+        const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        rres[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
+      }
+    } else {
+      const float* rp = reinterpret_cast<const float*>(p.res) + r0 * p.ldr + col;
+      const long long rs = 4 * p.ldr;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rres[i] = *reinterpret_cast<const float4*>(rp + i * rs);
+    }
+  }
+  float4 a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + rsub;
+    a[i] = *reinterpret_cast<const float4*>(st + r * 32 + ((cg ^ (r & 7)) << 2));
+    a[i].x += add4.x; a[i].y += add4.y; a[i].z += add4.z; a[i].w += add4.w;
+  }
+  if (p.rowvec && !rv_uniform) {
+    const int rpi = p.bw * p.bh;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int im = img0 + (4 * i) / rpi;  // img0 is the image of slot 0; rows advance by 4 per slot
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(im) * p.rowvec_ld + col));
+      a[i].x += r4.x; a[i].y += r4.y; a[i].z += r4.z; a[i].w += r4.w;
+    }
+  }
+  if (RES) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i].x += rres[i].x; a[i].y += rres[i].y; a[i].z += rres[i].z; a[i].w += rres[i].w; }
+  }
+  if (p.alpha != 1.0f) {
+    const float al = p.alpha;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i].x *= al; a[i].y *= al; a[i].z *= al; a[i].w *= al; }
+  }
+  if (F32) {
+    float* op = p.out_f32 + r0 * p.ld_f32 + col;
+    const long long os = 4 * p.ld_f32;
+    if (p.accumulate) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 o4 = *reinterpret_cast<const float4*>(op + i * os);
+        a[i].x += o4.x; a[i].y += o4.y; a[i].z += o4.z; a[i].w += o4.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(op + i * os) = a[i];
+  }
+  if (BF16) {
+    if (p.act == TNG_ACT_SILU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i].x = silu_f(a[i].x); a[i].y = silu_f(a[i].y); a[i].z = silu_f(a[i].z); a[i].w = silu_f(a[i].w); }
+    } else if (p.act == TNG_ACT_LRELU) {
+      const float sl = p.act_param;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a[i].x = a[i].x > 0.f ? a[i].x : a[i].x * sl; a[i].y = a[i].y > 0.f ? a[i].y : a[i].y * sl;
+        a[i].z = a[i].z > 0.f ? a[i].z : a[i].z * sl; a[i].w = a[i].w > 0.f ? a[i].w : a[i].w * sl;
+      }
+    }
+    __nv_bfloat16* op = p.out_bf16 + r0 * p.ld_bf16 + col;
+    const long long os = 4 * p.ld_bf16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint2 u;
+      u.x = pack_bf16(a[i].x, a[i].y); u.y = pack_bf16(a[i].z, a[i].w);
+      *reinterpret_cast<uint2*>(op + i * os) = u;
+    }
+    if (p.split_off > 0) {
+      op += p.split_off;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint2 l;
+        l.x = pack_bf16(a[i].x - __bfloat162float(__float2bfloat16_rn(a[i].x)), a[i].y - __bfloat162float(__float2bfloat16_rn(a[i].y)));
+        l.y = pack_bf16(a[i].z - __bfloat162float(__float2bfloat16_rn(a[i].z)), a[i].w - __bfloat162float(__float2bfloat16_rn(a[i].w)));
+        *reinterpret_cast<uint2*>(op + i * os) = l;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_stage(float* st, int lane, const uint32_t* v) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<uint4*>(st + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+template <int BN, bool RES, bool F32, bool BF16>
+__device__ __forceinline__ void epi_tile_full(const GemmKernelParams& p, float* st, long long r0, int img0, bool rv_uniform,
+                                              uint32_t taddr, int tn, int lane, int hf) {
+  const int cg = lane & 7, rsub = lane >> 3;
+#pragma unroll 1
+  for (int c = hf * 32; c < BN; c += 64) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c, v);
+    tmem_ld_wait();
+    __syncwarp();  // previous chunk's smem reads are complete
+    epi_stage(st, lane, v);
+    __syncwarp();
+    epi_chunk_full<RES, F32, BF16>(p, st, r0, img0, rsub, cg, tn * BN + c + 4 * cg, rv_uniform);
+  }
+}
+
+template <int BN, bool VEC>
+__device__ __noinline__ void epi_tile_generic(const GemmKernelParams& p, float* st, const EpiRows& R, uint32_t taddr, int tn,
+                                              int lane, int hf) {
+  const int cg = lane & 7, rsub = lane >> 3;
+#pragma unroll 1
+  for (int c = hf * 32; c < BN; c += 64) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c, v);
+    tmem_ld_wait();
+    __syncwarp();
+    epi_stage(st, lane, v);
+    __syncwarp();
+    epi_chunk<true, true, true, VEC>(p, st, R, rsub, cg, tn * BN + c + 4 * cg);
+  }
+}
+
+// GEGLU: columns [0, BN/2) of the tile are "hidden", [BN/2, BN) the matching "gate" (weights interleaved on the
+// host). out[:, tn*BN/2 + j] = (hid + b) * gelu_erf(gate + b'). Rows r0 + 4i (consecutive-row tiles); rows >= nvalid
+// are skipped.
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__device__ __forceinline__ void epi_tile_geglu(const GemmKernelParams& p, float* st, long long r0, int nleft,
+                                               uint32_t taddr, int tn, int lane, int hf) {
+  constexpr int HALF = BN / 2;
+  const int cg = lane & 7, rsub = lane >> 3;
+#pragma unroll 1
+  for (int c = hf * 32; c < HALF; c += 64) {
+    uint32_t v[32];
+    float4 hid[8];
+    tmem_ld32(taddr + c, v);
+    tmem_ld_wait();
+    __syncwarp();
+    epi_stage(st, lane, v);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + rsub;
+      hid[i] = *reinterpret_cast<const float4*>(st + r * 32 + ((cg ^ (r & 7)) << 2));
+    }
+    tmem_ld32(taddr + HALF + c, v);
+    tmem_ld_wait();
+    __syncwarp();
+    epi_stage(st, lane, v);
+    __syncwarp();
+    const int gcol = tn * BN + c + 4 * cg;  // GEMM column of the hidden half; gate at + HALF
+    const int ocol = tn * HALF + c + 4 * cg;
+    float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
+    if (p.bias) {
+      bh = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+      bg = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + HALF));
+    }
+    __nv_bfloat16* op = p.out_bf16 + r0 * p.ld_bf16 + ocol;
+    const long long os = 4 * p.ld_bf16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + rsub;
+      const float4 g = *reinterpret_cast<const float4*>(st + r * 32 + ((cg ^ (r & 7)) << 2));
+      if (4 * i >= nleft) continue;
+      const float y0 = (hid[i].x + bh.x) * gelu_erf_f(g.x + bg.x);
+      const float y1 = (hid[i].y + bh.y) * gelu_erf_f(g.y + bg.y);
+      const float y2 = (hid[i].z + bh.z) * gelu_erf_f(g.z + bg.z);
+      const float y3 = (hid[i].w + bh.w) * gelu_erf_f(g.w + bg.w);
+      uint2 u;
+      u.x = pack_bf16(y0, y1); u.y = pack_bf16(y2, y3);
+      *reinterpret_cast<uint2*>(op + i * os) = u;
+      if (p.split_off > 0) {
+        uint2 l;
+        l.x = pack_bf16(y0 - __bfloat162float(__float2bfloat16_rn(y0)), y1 - __bfloat162float(__float2bfloat16_rn(y1)));
+        l.y = pack_bf16(y2 - __bfloat162float(__float2bfloat16_rn(y2)), y3 - __bfloat162float(__float2bfloat16_rn(y3)));
+        *reinterpret_cast<uint2*>(op + p.split_off + i * os) = l;
+      }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUtensorMap amap1,
                const __grid_constant__ CUtensorMap amap2, const __grid_constant__ CUtensorMap amap3,
                const __grid_constant__ CUtensorMap bmap, const __grid_constant__ GemmKernelParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment (checked below)
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* sEpi = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -91,6 +430,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("[tng] gemm_tc: dynamic smem base not 1024-byte aligned\n");
+      __trap();
+    }
     tma_prefetch_desc(&amap0);
     tma_prefetch_desc(&bmap);
     for (int s = 0; s < STAGES; ++s) {
@@ -99,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -116,7 +459,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     // ===================================================== TMA producer
-    const CUtensorMap* amaps[4] = {&amap0, &amap1, &amap2, &amap3};
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -127,7 +469,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tb * p.bn;
       for (int gi = 0; gi < p.n_groups; ++gi) {
         const KGroupDev g = p.g[gi];
-        const CUtensorMap* am = amaps[g.view];
+        const CUtensorMap* am = g.view == 0 ? &amap0 : g.view == 1 ? &amap1 : g.view == 2 ? &amap2 : &amap3;
         for (int kb = 0; kb < g.nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -165,9 +507,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       umma_commit(&tfull_bar[as]);
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue
-    const int ew = warp & 3;           // TMEM lane quarter this warp may access
-    const int r = ew * 32 + lane;      // row inside the 128-row tile
+    // ===================================================== epilogue (8 warps)
+    const int ew = warp & 3;            // TMEM lane quarter this warp may access
+    const int hf = (warp - 4) >> 2;     // which half of the 32-column chunks
+    float* st = sEpi + (warp - 4) * (32 * 32);
+    const int rsub = lane >> 3;
+    const int mode = (p.res ? 1 : 0) | (p.out_f32 ? 2 : 0) | (p.out_bf16 ? 4 : 0);
     const bool geglu = (p.act == TNG_ACT_GEGLU);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -175,189 +520,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       const int tw = tm % p.tiles_w;
       const int th = (tm / p.tiles_w) % p.tiles_h;
       const int tb = tm / (p.tiles_w * p.tiles_h);
-      const int w = tw * p.bw + (r % p.bw);
-      const int h = th * p.bh + (r / p.bw) % p.bh;
-      const int img = tb * p.bn + r / (p.bw * p.bh);
-      const bool row_ok = (w < p.W) && (h < p.H) && (img < p.NB);
-      const long long row = (static_cast<long long>(img) * p.H + h) * p.W + w;
-
+      // rows of a tile are consecutive output rows; valid rows form a prefix (see host tiling)
+      const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tb * p.bn;
+      const long long row_base = (static_cast<long long>(n0) * p.H + h0) * p.W + w0;
+      int nvalid;
+      if (p.bh == 1 && p.bn == 1) nvalid = min(BM, p.W - w0);
+      else if (p.bn == 1) nvalid = min(p.bh, p.H - h0) * p.bw;
+      else nvalid = min(p.bn, p.NB - n0) * p.bh * p.bw;
+      const int rpi = p.bw * p.bh;  // rows of one image inside a tile
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (static_cast<uint32_t>(ew * 32) << 16);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (static_cast<uint32_t>(ew * 32) << 16);
-
-      if (!geglu) {
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+      const bool full = p.fast_epi && (nvalid == BM) && ((tn + 1) * BN <= p.Ncols);
+      if (p.dbg == 1) {
+        // experiment: no epilogue work at all
+      } else if (p.dbg == 2) {
+        for (int c = hf * 32; c < BN; c += 64) {
           uint32_t v[32];
-          __syncwarp();
           tmem_ld32(taddr + c, v);
           tmem_ld_wait();
-          const int col0 = tn * BN + c;
-          if (!row_ok || col0 >= p.Ncols) continue;
-          const int ncol = min(32, p.Ncols - col0);
-          float x[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-          const bool vec = p.vec_ok && (ncol == 32);
-          if (p.bias) {
-            if (vec) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                x[j] += b4.x; x[j + 1] += b4.y; x[j + 2] += b4.z; x[j + 3] += b4.w;
-              }
-            } else {
-              for (int j = 0; j < ncol; ++j) x[j] += __ldg(p.bias + col0 + j);
-            }
-          }
-          if (p.rowvec) {
-            const float* rv = p.rowvec + static_cast<long long>(img) * p.rowvec_ld + col0;
-            if (vec) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + j));
-                x[j] += b4.x; x[j + 1] += b4.y; x[j + 2] += b4.z; x[j + 3] += b4.w;
-              }
-            } else {
-              for (int j = 0; j < ncol; ++j) x[j] += __ldg(rv + j);
-            }
-          }
-          if (p.res) {
-            if (p.res_bf16) {
-              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + row * p.ldr + col0;
-              if (vec) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
-                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float2 f = __bfloat1622float2(h2[q]);
-                    x[j + 2 * q] += f.x; x[j + 2 * q + 1] += f.y;
-                  }
-                }
-              } else {
-                for (int j = 0; j < ncol; ++j) x[j] += __bfloat162float(rp[j]);
-              }
-            } else {
-              const float* rp = reinterpret_cast<const float*>(p.res) + row * p.ldr + col0;
-              if (vec) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 b4 = *reinterpret_cast<const float4*>(rp + j);
-                  x[j] += b4.x; x[j + 1] += b4.y; x[j + 2] += b4.z; x[j + 3] += b4.w;
-                }
-              } else {
-                for (int j = 0; j < ncol; ++j) x[j] += rp[j];
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] *= p.alpha;
-          if (p.out_f32) {
-            float* op = p.out_f32 + row * p.ld_f32 + col0;
-            if (vec) {
-              if (p.accumulate) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 o4 = *reinterpret_cast<const float4*>(op + j);
-                  x[j] += o4.x; x[j + 1] += o4.y; x[j + 2] += o4.z; x[j + 3] += o4.w;
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(op + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-            } else {
-              for (int j = 0; j < ncol; ++j) {
-                if (p.accumulate) x[j] += op[j];
-                op[j] = x[j];
-              }
-            }
-          }
-          if (p.out_bf16) {
-            __nv_bfloat16* op = p.out_bf16 + row * p.ld_bf16 + col0;
-            float y[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = apply_act(x[j], p.act, p.act_param);
-            if (vec) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                u.x = pack_bf16(y[j], y[j + 1]); u.y = pack_bf16(y[j + 2], y[j + 3]);
-                u.z = pack_bf16(y[j + 4], y[j + 5]); u.w = pack_bf16(y[j + 6], y[j + 7]);
-                *reinterpret_cast<uint4*>(op + j) = u;
-              }
-              if (p.split_off > 0) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  float l[8];
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) l[q] = y[j + q] - __bfloat162float(__float2bfloat16_rn(y[j + q]));
-                  uint4 u;
-                  u.x = pack_bf16(l[0], l[1]); u.y = pack_bf16(l[2], l[3]);
-                  u.z = pack_bf16(l[4], l[5]); u.w = pack_bf16(l[6], l[7]);
-                  *reinterpret_cast<uint4*>(op + p.split_off + j) = u;
-                }
-              }
-            } else {
-              for (int j = 0; j < ncol; ++j) {
-                const __nv_bfloat16 hi = __float2bfloat16_rn(y[j]);
-                op[j] = hi;
-                if (p.split_off > 0) op[p.split_off + j] = __float2bfloat16_rn(y[j] - __bfloat162float(hi));
-              }
-            }
-          }
+          if (v[0] == 0x7fc12345u && v[7] == 0x12345u) st[lane] = __uint_as_float(v[3]);
         }
+      } else if (geglu) {
+        // slot i of this lane is row ew*32 + rsub + 4i; rows below nvalid are valid
+        epi_tile_geglu<BN>(p, st, row_base + ew * 32 + rsub, nvalid - (ew * 32 + rsub), taddr, tn, lane, hf);
+      } else if (!full) {
+        EpiRows R;
+        R.valid = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = ew * 32 + 4 * i + rsub;
+          R.img[i] = n0 + rr / rpi;
+          R.row[i] = row_base + rr;
+          if (rr < nvalid) R.valid |= 1u << i;
+        }
+        if (p.fast_epi) epi_tile_generic<BN, true>(p, st, R, taddr, tn, lane, hf);
+        else epi_tile_generic<BN, false>(p, st, R, taddr, tn, lane, hf);
       } else {
-        // GEGLU: columns [0, BN/2) of the tile are "hidden", [BN/2, BN) the matching "gate" (weights interleaved
-        // on the host). out[:, tn*BN/2 + j] = (hid + b) * gelu_erf(gate + b')
-        constexpr int HALF = BN / 2;
-#pragma unroll 1
-        for (int c = 0; c < HALF; c += 32) {
-          uint32_t vh[32], vg[32];
-          __syncwarp();
-          tmem_ld32(taddr + c, vh);
-          tmem_ld32(taddr + HALF + c, vg);
-          tmem_ld_wait();
-          if (!row_ok) continue;
-          const int gcol = tn * BN + c;  // GEMM column of hidden; gate at gcol + HALF
-          const int ocol = tn * HALF + c;
-          __nv_bfloat16* op = p.out_bf16 + row * p.ld_bf16 + ocol;
-          float y[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float hv = __uint_as_float(vh[j]);
-            float gv = __uint_as_float(vg[j]);
-            if (p.bias) {
-              hv += __ldg(p.bias + gcol + j);
-              gv += __ldg(p.bias + gcol + HALF + j);
-            }
-            y[j] = hv * gelu_erf_f(gv);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 u;
-            u.x = pack_bf16(y[j], y[j + 1]); u.y = pack_bf16(y[j + 2], y[j + 3]);
-            u.z = pack_bf16(y[j + 4], y[j + 5]); u.w = pack_bf16(y[j + 6], y[j + 7]);
-            *reinterpret_cast<uint4*>(op + j) = u;
-          }
-          if (p.split_off > 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float l[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) l[q] = y[j + q] - __bfloat162float(__float2bfloat16_rn(y[j + q]));
-              uint4 u;
-              u.x = pack_bf16(l[0], l[1]); u.y = pack_bf16(l[2], l[3]);
-              u.z = pack_bf16(l[4], l[5]); u.w = pack_bf16(l[6], l[7]);
-              *reinterpret_cast<uint4*>(op + p.split_off + j) = u;
-            }
-          }
+        const long long r0 = row_base + ew * 32 + rsub;
+        const int img0 = n0 + (ew * 32 + rsub) / rpi;
+        const bool rv_uniform = (rpi % 32) == 0;   // the warp's 32 rows lie in one image
+        switch (mode) {
+          case 2: epi_tile_full<BN, false, true, false>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf); break;
+          case 3: epi_tile_full<BN, true, true, false>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf); break;
+          case 4: epi_tile_full<BN, false, false, true>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf); break;
+          case 5: epi_tile_full<BN, true, false, true>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf); break;
+          case 6: epi_tile_full<BN, false, true, true>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf); break;
+          default: epi_tile_full<BN, true, true, true>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf); break;
         }
       }
-      // all tcgen05.ld of this warp are complete (wait::ld above): hand the accumulator stage back
+      // all tcgen05.ld of this warp are complete (wait::ld): hand the accumulator stage back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -385,7 +599,7 @@ static int launch_gemm(const CUtensorMap* am, const CUtensorMap& bm, const GemmK
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, st>>>(am[0], am[1], am[2], am[3], bm, p);
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(am[0], am[1], am[2], am[3], bm, p);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(TNG_ECUDA, "gemm_tc<%d> launch: %s", BN, cudaGetErrorString(e));
@@ -481,6 +695,12 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   if (d->out_f32 && (!al16(d->out_f32) || d->ld_f32 % 4)) vec = false;
   if (d->out_bf16 && (!al16(d->out_bf16) || d->ld_bf16 % 8 || d->split_off % 8)) vec = false;
   p.vec_ok = vec ? 1 : 0;
+  p.fast_epi = (vec && d->Ncols % 4 == 0) ? 1 : 0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("TNG_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+  }
   if (d->act == TNG_ACT_GEGLU && !vec) return set_error(TNG_EINVAL, "GEGLU epilogue needs 16-byte aligned output");
 
   // tensor maps
