@@ -47,6 +47,30 @@ __device__ __forceinline__ float warp_max(float v) {
 // consecutive 16-byte quads of a row (coalesced) and the per-channel constants live in registers.
 constexpr int GN_ROWS = 128;  // pixels per CTA
 
+template <bool BF>
+__device__ __forceinline__ float4 ld_quad(const void* base, long long idx) {
+  if (BF) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+}
+
+template <bool BF>
+__device__ __forceinline__ void gn_accum(const void* base, long long idx0, long long stride, int rl, int nrows, int RL,
+                                         float* s, float* ss) {
+  long long idx = idx0 + rl * stride;
+  const long long step = RL * stride;
+#pragma unroll 4
+  for (int r = rl; r < nrows; r += RL, idx += step) {
+    const float4 v = ld_quad<BF>(base, idx);
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]); ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
+  }
+}
+
 __global__ void __launch_bounds__(256) gn_stats_kernel(const void* x0, int dt0, int C0, const void* x1, int dt1, int C1,
                                                         long long HW, int groups, double* stats) {
   __shared__ float s_sum[64], s_sq[64];
@@ -70,13 +94,9 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* x0, int dt0, 
       const int Cs = first ? C0 : C1;
       const int cc = first ? c : c - C0;
       float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-      const long long rbase = n * HW + r0;
-#pragma unroll 4
-      for (int r = rl; r < nrows; r += RL) {
-        const float4 v = load4(base, dt, (rbase + r) * Cs + cc);
-        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-        ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
-      }
+      const long long idx0 = (n * HW + r0) * Cs + cc;
+      if (dt == TNG_DT_F32) gn_accum<false>(base, idx0, Cs, rl, nrows, RL, s, ss);
+      else gn_accum<true>(base, idx0, Cs, rl, nrows, RL, s, ss);
       const int g0 = c / cpg, g3 = (c + 3) / cpg;
       if (g0 == g3) {
         atomicAdd(&s_sum[g0], (s[0] + s[1]) + (s[2] + s[3]));
@@ -98,9 +118,36 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* x0, int dt0, 
   }
 }
 
+template <bool BF, bool SILU, bool SPLIT, bool RAW>
+__device__ __forceinline__ void gn_apply_rows(const void* base, long long idx0, long long stride, int rl, int nrows, int RL,
+                                              const float* sc, const float* sh, __nv_bfloat16* y, long long ystride,
+                                              int split_off, __nv_bfloat16* raw, long long rstride, int raw_split_off) {
+  long long idx = idx0 + rl * stride;
+  const long long step = RL * stride;
+  y += rl * ystride;
+  const long long ystep = RL * ystride;
+  if (RAW) raw += rl * rstride;
+  const long long rstep = RL * rstride;
+#pragma unroll 4
+  for (int r = rl; r < nrows; r += RL, idx += step, y += ystep) {
+    const float4 v = ld_quad<BF>(base, idx);
+    float4 o;
+    o.x = fmaf(v.x, sc[0], sh[0]); o.y = fmaf(v.y, sc[1], sh[1]); o.z = fmaf(v.z, sc[2], sh[2]); o.w = fmaf(v.w, sc[3], sh[3]);
+    if (SILU) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+    store4_bf16(y, o);
+    if (SPLIT) store4_bf16(y + split_off, make_float4(bf16_lo(o.x), bf16_lo(o.y), bf16_lo(o.z), bf16_lo(o.w)));
+    if (RAW) {
+      store4_bf16(raw, v);
+      if (SPLIT) store4_bf16(raw + raw_split_off, make_float4(bf16_lo(v.x), bf16_lo(v.y), bf16_lo(v.z), bf16_lo(v.w)));
+      raw += rstep;
+    }
+  }
+}
+
+template <bool SILU, bool SPLIT, bool RAW>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, int C0, const void* x1, int dt1, int C1,
                                                         long long HW, int groups, const double* stats,
-                                                        const float* gamma, const float* beta, float eps, int act,
+                                                        const float* gamma, const float* beta, float eps,
                                                         __nv_bfloat16* y, long long ld_y, int split_off,
                                                         __nv_bfloat16* raw, long long ld_raw, int raw_split_off) {
   __shared__ float s_mean[64], s_rstd[64];
@@ -142,19 +189,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, 
       sc[j] = s_rstd[g] * gm[j];
       sh[j] = bt[j] - s_mean[g] * sc[j];
     }
-    const long long rbase = n * HW + r0;
-#pragma unroll 4
-    for (int r = rl; r < nrows; r += RL) {
-      const long long row = rbase + r;
-      const float4 v = load4(base, dt, row * Cs + cc);
-      float4 o;
-      o.x = act_f(v.x * sc[0] + sh[0], act, 0.f);
-      o.y = act_f(v.y * sc[1] + sh[1], act, 0.f);
-      o.z = act_f(v.z * sc[2] + sh[2], act, 0.f);
-      o.w = act_f(v.w * sc[3] + sh[3], act, 0.f);
-      store4_split(y + row * ld_y + c, o, split_off);
-      if (raw) store4_split(raw + row * ld_raw + c, v, raw_split_off);
-    }
+    const long long rowb = n * HW + r0;
+    __nv_bfloat16* yp = y + rowb * ld_y + c;
+    __nv_bfloat16* rp = RAW ? raw + rowb * ld_raw + c : nullptr;
+    if (dt == TNG_DT_F32)
+      gn_apply_rows<false, SILU, SPLIT, RAW>(base, rowb * Cs + cc, Cs, rl, nrows, RL, sc, sh, yp, ld_y, split_off, rp, ld_raw, raw_split_off);
+    else
+      gn_apply_rows<true, SILU, SPLIT, RAW>(base, rowb * Cs + cc, Cs, rl, nrows, RL, sc, sh, yp, ld_y, split_off, rp, ld_raw, raw_split_off);
   }
 }
 
@@ -443,9 +484,21 @@ extern "C" int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, cons
   if (!x0 || !stats || !y || C % groups || C0 % 4 || (x1 && C1 % 4) || ld_y % 4 || split_off % 4 || C > 8192)
     return set_error(TNG_EINVAL, "groupnorm_apply: bad shape");
   dim3 grid((unsigned)((HW + GN_ROWS - 1) / GN_ROWS), (unsigned)NB);
-  gn_apply_kernel<<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, x1, dt1, x1 ? (int)C1 : 0, HW, groups, stats, gamma,
-                                                    beta, eps, act, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off,
-                                                    reinterpret_cast<__nv_bfloat16*>(raw_bf16), ld_raw, raw_split_off);
+  if (act != TNG_ACT_NONE && act != TNG_ACT_SILU) return set_error(TNG_EINVAL, "groupnorm_apply: act must be NONE or SILU");
+  const bool silu = act == TNG_ACT_SILU, split = split_off > 0, hasraw = raw_bf16 != nullptr;
+#define TNG_GN_LAUNCH(S, P, R)                                                                                          \
+  gn_apply_kernel<S, P, R><<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, x1, dt1, x1 ? (int)C1 : 0, HW, groups, stats, \
+                                                          gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y,   \
+                                                          split_off, reinterpret_cast<__nv_bfloat16*>(raw_bf16), ld_raw, \
+                                                          raw_split_off)
+  if (silu) {
+    if (split) { if (hasraw) TNG_GN_LAUNCH(true, true, true); else TNG_GN_LAUNCH(true, true, false); }
+    else { if (hasraw) TNG_GN_LAUNCH(true, false, true); else TNG_GN_LAUNCH(true, false, false); }
+  } else {
+    if (split) { if (hasraw) TNG_GN_LAUNCH(false, true, true); else TNG_GN_LAUNCH(false, true, false); }
+    else { if (hasraw) TNG_GN_LAUNCH(false, false, true); else TNG_GN_LAUNCH(false, false, false); }
+  }
+#undef TNG_GN_LAUNCH
   count_launch();
   return check_launch("gn_apply");
 }

@@ -76,7 +76,9 @@ def test_tiny_inference_vs_golden(cuda, precision):
                         prompt_embeds=torch.from_numpy(gd["embeds"]), boolean_prompt_mask=torch.from_numpy(gd["mask"]),
                         latents=torch.from_numpy(gd["lat0"]), noises=noises, latent_shape=(32, 16))
     # (GroupNorm statistics are reduced with atomics, so the two runs agree to round-off, not bit for bit)
-    assert rel(lat, lat2) < 1e-4
+    # split mode: round-off only; bf16 mode: a flipped bf16 rounding decorrelates the two runs at the same level as
+    # each one's distance to the fp32 reference
+    assert rel(lat, lat2) < (1e-4 if precision == "split" else 6e-2)
 
 
 def test_scheduler_step_bit_exact(cuda):
