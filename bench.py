@@ -99,47 +99,106 @@ def synthetic_inputs(B: int, tokens: int, dim: int, rank: int):
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
+def pick_threads():
+    """Host threads for the CPU arm: the fastest of a few counts on a representative 3x3 conv (oversubscribing a
+    128-core box makes torch's CPU kernels several times slower, so 'all cores' is not 'all the threads it can use')."""
+    import torch.nn.functional as F
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    x = torch.randn(2, 320, 256, 16)
+    w = torch.randn(320, 320, 3, 3)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        F.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            F.conv2d(x, w, padding=1)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
+class CpuReference:
+    """The reference's CPU arithmetic for the path (oracle port, see oracle/__init__.py) on bounded samples."""
+
+    def __init__(self, args):
+        from oracle import hifigan as ohifi
+        from oracle import unet as ounet
+        from oracle import vae as ovae
+        from tango_b200 import synth
+        torch.set_grad_enabled(False)
+        self.args, self.ounet, self.ovae, self.ohifi, self.synth = args, ounet, ovae, ohifi, synth
+        self.cores = pick_threads()
+        self.cfg = synth.BASE_UNET_CONFIG
+        self.usd = synth.synth_state_dict(synth.unet_param_shapes(self.cfg), 0)
+        self.vsd = synth.synth_state_dict(synth.vae_decoder_param_shapes(), 0)
+        self.embeds, self.mask = synthetic_inputs(1, args.tokens, self.cfg["cross_attention_dim"], 0)
+        g = torch.Generator().manual_seed(1234)
+        self.x_full = torch.randn(2, 8, 256, 16, generator=g)
+        self.x_small = self.x_full[:, :, :64].contiguous()
+        # calibration on the quarter-length clip, FLOPs counted live
+        from torch.utils.flop_counter import FlopCounterMode
+        with FlopCounterMode(display=False) as fc:
+            t0 = time.perf_counter()
+            self.fwd(self.x_small, 0)
+            self.t_small = time.perf_counter() - t0
+        self.f_small = float(fc.get_total_flops())
+        self.f_full = 2 * F_UNET          # CFG batch 2
+        self.use_full = self.t_small * self.f_full / self.f_small <= 25.0
+
+    def fwd(self, x, i):
+        return self.ounet.unet_forward(self.usd, self.cfg, x, torch.tensor(995 - 5 * (i % 199)), self.embeds, self.mask)
+
+    def step_seconds(self, i):
+        """Seconds of one CFG UNet forward for one prompt at 256x16 (measured, or FLOP-scaled from the 64x16 sample)."""
+        x = self.x_full if self.use_full else self.x_small
+        t0 = time.perf_counter()
+        self.fwd(x, i)
+        dt = time.perf_counter() - t0
+        return dt if self.use_full else dt * self.f_full / self.f_small
+
+    def decode_seconds(self):
+        """VAE decoder + HiFi-GAN for one sample; a quarter-length latent scaled by 4 when the box is slow."""
+        z = self.x_full[:1] if self.use_full else self.x_small[:1]
+        t0 = time.perf_counter()
+        mel = self.ovae.decode_first_stage(self.vsd, z, self.synth.VAE_CONFIG["scale_factor"])
+        self.ohifi.decode_to_waveform(self.vsd, mel)
+        dt = time.perf_counter() - t0
+        return dt if self.use_full else dt * 4.0
+
+    def describe(self, t_fwd, t_dec):
+        a = self.args
+        what = ("1 UNet forward at CFG batch 2 (1 prompt, 64 tokens, 256x16 latent)" if self.use_full else
+                f"1 UNet forward at CFG batch 2 on a quarter-length latent (64x16, {self.f_small / 1e9:.0f} GFLOP counted live) "
+                f"scaled by the FLOP ratio to the 256x16 forward ({self.f_full / 1e9:.0f} GFLOP)")
+        return (f"oracle port, torch CPU fp32, {self.cores} threads: per step {what} = {t_fwd:.2f} s; VAE+HiFi-GAN for 1 sample "
+                f"= {t_dec:.2f} s (timed once); extrapolated linearly to {a.denoise_steps} denoising steps and batch {a.batch}")
+
+
 def run_reference(args):
-    """The reference's CPU arithmetic for this path (oracle port, all host threads) on a bounded sample per step."""
+    """`--impl reference`: the reference's CPU arithmetic for this path on the box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import hifigan as ohifi
-    from oracle import unet as ounet
-    from oracle import vae as ovae
-    from tango_b200 import synth
-    torch.set_grad_enabled(False)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = synth.BASE_UNET_CONFIG
-    usd = synth.synth_state_dict(synth.unet_param_shapes(cfg), 0)
-    vsd = synth.synth_state_dict(synth.vae_decoder_param_shapes(), 0)
-    embeds, mask = synthetic_inputs(1, args.tokens, cfg["cross_attention_dim"], 0)
-    g = torch.Generator().manual_seed(1234)
-    x = torch.randn(2, 8, 256, 16, generator=g)
-    # decode stage timed once (it is 0.5 % of the job): one sample through VAE decoder + HiFi-GAN
-    t0 = time.perf_counter()
-    mel = ovae.decode_first_stage(vsd, x[:1], synth.VAE_CONFIG["scale_factor"])
-    ohifi.decode_to_waveform(vsd, mel)
-    t_dec = time.perf_counter() - t0
+    ref = CpuReference(args)
+    t_dec = ref.decode_seconds()
     times = []
     for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        ounet.unet_forward(usd, cfg, x, torch.tensor(995 - 5 * i), embeds, mask)
-        dt = time.perf_counter() - t0
+        dt = ref.step_seconds(i)
         if i >= args.warmup:
             times.append(dt)
     t_fwd = float(np.mean(times))
-    per_sample = args.denoise_steps * t_fwd + t_dec       # CFG forward at UNet batch 2 = one prompt
+    per_sample = args.denoise_steps * t_fwd + t_dec       # one prompt = one CFG forward per denoising step
     value = AUDIO_S_PER_SAMPLE / per_sample
-    sample = (f"per step: 1 UNet forward at CFG batch 2 (1 prompt, 64 tokens) = {t_fwd:.2f} s; VAE+HiFi-GAN for 1 sample "
-              f"timed once = {t_dec:.2f} s; extrapolated linearly to {args.denoise_steps} steps (per-step cost is "
-              f"step-independent) and to batch {args.batch} (CPU throughput is batch-independent)")
     line = {"impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_sample * args.batch * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, 1),
-            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": ref.cores, "kind": "port",
+                             "sample": ref.describe(t_fwd, t_dec)},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -289,28 +348,11 @@ def run_ours(args):
 
 
 def cpu_baseline(args):
-    from oracle import hifigan as ohifi
-    from oracle import unet as ounet
-    from oracle import vae as ovae
-    from tango_b200 import synth
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = synth.BASE_UNET_CONFIG
-    usd = synth.synth_state_dict(synth.unet_param_shapes(cfg), 0)
-    vsd = synth.synth_state_dict(synth.vae_decoder_param_shapes(), 0)
-    embeds, mask = synthetic_inputs(1, args.tokens, cfg["cross_attention_dim"], 0)
-    x = torch.randn(2, 8, 256, 16, generator=torch.Generator().manual_seed(1234))
-    t0 = time.perf_counter()
-    ounet.unet_forward(usd, cfg, x, torch.tensor(995), embeds, mask)
-    t_fwd = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    mel = ovae.decode_first_stage(vsd, x[:1], synth.VAE_CONFIG["scale_factor"])
-    ohifi.decode_to_waveform(vsd, mel)
-    t_dec = time.perf_counter() - t0
+    ref = CpuReference(args)
+    t_fwd = ref.step_seconds(0)
+    t_dec = ref.decode_seconds()
     v = AUDIO_S_PER_SAMPLE / (args.denoise_steps * t_fwd + t_dec)
-    return {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
-            "sample": f"oracle port (torch CPU fp32): 1 UNet forward at CFG batch 2 = {t_fwd:.2f} s, VAE+HiFi-GAN for 1 sample = "
-                      f"{t_dec:.2f} s; extrapolated to {args.denoise_steps} steps x batch {args.batch}"}
+    return {"value": v, "unit": "audio-s/s", "cores": ref.cores, "kind": "port", "sample": ref.describe(t_fwd, t_dec)}
 
 
 def main():
