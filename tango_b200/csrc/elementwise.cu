@@ -45,7 +45,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // Thread layout: a CTA owns GN_ROWS pixels of one image; thread t keeps a FIXED channel quad q = t % QT and walks the
 // rows r = t / QT, + RL, ... (QT = min(C/4, 256) quad threads, RL = 256 / QT row lanes), so consecutive threads read
 // consecutive 16-byte quads of a row (coalesced) and the per-channel constants live in registers.
-constexpr int GN_ROWS = 128;  // pixels per CTA
+constexpr int GN_ROWS_MAX = 128;  // pixels per CTA (upper bound; the host shrinks it for small grids)
 
 template <bool BF>
 __device__ __forceinline__ float4 ld_quad(const void* base, long long idx) {
@@ -72,7 +72,7 @@ __device__ __forceinline__ void gn_accum(const void* base, long long idx0, long 
 }
 
 __global__ void __launch_bounds__(256) gn_stats_kernel(const void* x0, int dt0, int C0, const void* x1, int dt1, int C1,
-                                                        long long HW, int groups, double* stats) {
+                                                        long long HW, int groups, double* stats, int GN_ROWS) {
   __shared__ float s_sum[64], s_sq[64];
   const int n = blockIdx.y;
   const long long r0 = static_cast<long long>(blockIdx.x) * GN_ROWS;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, 
                                                         long long HW, int groups, const double* stats,
                                                         const float* gamma, const float* beta, float eps,
                                                         __nv_bfloat16* y, long long ld_y, int split_off,
-                                                        __nv_bfloat16* raw, long long ld_raw, int raw_split_off) {
+                                                        __nv_bfloat16* raw, long long ld_raw, int raw_split_off, int GN_ROWS) {
   __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.y;
   const int C = C0 + C1;
@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, 
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// one warp per row; the row is cached in registers (C <= 2048) so the variance is the exact two-pass form.
+// one warp per row; the row is cached in registers (NI float4 per lane, C <= 128 * NI) so the variance is the exact
+// two-pass form; NI is a template parameter so that no predicated-off iterations are issued.
+template <int NI>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long long rows, int C, const float* gamma,
                                                          const float* beta, float eps, __nv_bfloat16* y, long long ld_y,
                                                          int split_off) {
@@ -208,20 +210,19 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long lon
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int Q = C / 4;
-  float4 v[16];
+  float4 v[NI];
   float s = 0.f;
+  const float* xr = x + row * C;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < NI; ++i) {
     const int q = lane + i * 32;
-    if (q < Q) {
-      v[i] = *reinterpret_cast<const float4*>(x + row * C + q * 4);
-      s += v[i].x + v[i].y + v[i].z + v[i].w;
-    }
+    v[i] = (q < Q) ? *reinterpret_cast<const float4*>(xr + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mean = warp_sum(s) / C;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < NI; ++i) {
     const int q = lane + i * 32;
     if (q < Q) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
@@ -229,8 +230,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long lon
     }
   }
   const float rstd = rsqrtf(warp_sum(sq) / C + eps);
+  __nv_bfloat16* yr = y + row * ld_y;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < NI; ++i) {
     const int q = lane + i * 32;
     if (q < Q) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + q * 4));
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long lon
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z;
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      store4_split(y + row * ld_y + q * 4, o, split_off);
+      store4_split(yr + q * 4, o, split_off);
     }
   }
 }
@@ -450,6 +452,15 @@ __global__ void tanh_to_i16_kernel(const float* x, long long n, long long ld_x, 
   }
 }
 
+// pixels per GroupNorm CTA: enough CTAs (>= 4 per SM) even on the small-spatial levels
+static inline int gn_rows_for(long long NB, long long HW) {
+  long long rows = (NB * HW + 4LL * num_sms() - 1) / (4LL * num_sms());
+  if (rows < 8) rows = 8;
+  if (rows > GN_ROWS_MAX) rows = GN_ROWS_MAX;
+  if (rows > HW) rows = HW;
+  return static_cast<int>(rows);
+}
+
 static inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -470,8 +481,9 @@ extern "C" int tng_groupnorm_stats(const void* x0, int32_t dt0, int64_t C0, cons
     return set_error(TNG_EINVAL, "groupnorm_stats: bad shape C0=%lld C1=%lld groups=%d", (long long)C0, (long long)C1, groups);
   cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * NB * groups, ST(stream));
   if (e != cudaSuccess) return set_error(TNG_ECUDA, "memset: %s", cudaGetErrorString(e));
-  dim3 grid((unsigned)((HW + GN_ROWS - 1) / GN_ROWS), (unsigned)NB);
-  gn_stats_kernel<<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, x1, dt1, x1 ? (int)C1 : 0, HW, groups, stats);
+  const int gn_rows = gn_rows_for(NB, HW);
+  dim3 grid((unsigned)((HW + gn_rows - 1) / gn_rows), (unsigned)NB);
+  gn_stats_kernel<<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, x1, dt1, x1 ? (int)C1 : 0, HW, groups, stats, gn_rows);
   count_launch();
   return check_launch("gn_stats");
 }
@@ -483,14 +495,15 @@ extern "C" int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, cons
   const int64_t C = C0 + (x1 ? C1 : 0);
   if (!x0 || !stats || !y || C % groups || C0 % 4 || (x1 && C1 % 4) || ld_y % 4 || split_off % 4 || C > 8192)
     return set_error(TNG_EINVAL, "groupnorm_apply: bad shape");
-  dim3 grid((unsigned)((HW + GN_ROWS - 1) / GN_ROWS), (unsigned)NB);
+  const int gn_rows = gn_rows_for(NB, HW);
+  dim3 grid((unsigned)((HW + gn_rows - 1) / gn_rows), (unsigned)NB);
   if (act != TNG_ACT_NONE && act != TNG_ACT_SILU) return set_error(TNG_EINVAL, "groupnorm_apply: act must be NONE or SILU");
   const bool silu = act == TNG_ACT_SILU, split = split_off > 0, hasraw = raw_bf16 != nullptr;
 #define TNG_GN_LAUNCH(S, P, R)                                                                                          \
   gn_apply_kernel<S, P, R><<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, x1, dt1, x1 ? (int)C1 : 0, HW, groups, stats, \
                                                           gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y,   \
                                                           split_off, reinterpret_cast<__nv_bfloat16*>(raw_bf16), ld_raw, \
-                                                          raw_split_off)
+                                                          raw_split_off, gn_rows)
   if (silu) {
     if (split) { if (hasraw) TNG_GN_LAUNCH(true, true, true); else TNG_GN_LAUNCH(true, true, false); }
     else { if (hasraw) TNG_GN_LAUNCH(true, false, true); else TNG_GN_LAUNCH(true, false, false); }
@@ -507,8 +520,16 @@ extern "C" int tng_layernorm(const float* x, int64_t rows, int64_t C, const floa
                              void* y, int64_t ld_y, int32_t split_off, void* stream) {
   if (!x || !y || C % 4 || C > 2048 || ld_y % 4 || split_off % 4) return set_error(TNG_EINVAL, "layernorm: C=%lld unsupported", (long long)C);
   const int wpb = 8;
-  layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, ST(stream)>>>(
-      x, rows, (int)C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off);
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  const int ni = (int)((C / 4 + 31) / 32);
+#define TNG_LN(NI) layernorm_kernel<NI><<<grid, wpb * 32, 0, ST(stream)>>>(x, rows, (int)C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off)
+  if (ni <= 1) TNG_LN(1);
+  else if (ni <= 2) TNG_LN(2);
+  else if (ni <= 3) TNG_LN(3);
+  else if (ni <= 5) TNG_LN(5);
+  else if (ni <= 10) TNG_LN(10);
+  else TNG_LN(16);
+#undef TNG_LN
   count_launch();
   return check_launch("layernorm");
 }

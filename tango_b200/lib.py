@@ -148,6 +148,9 @@ class _Profiler:
 
 PROF = _Profiler()
 
+# profiling experiments only (tools/ablate.py): TNG_SKIP=gn,ln,attn,gemm makes the named launches no-ops
+_SKIP = set(filter(None, os.environ.get("TNG_SKIP", "").split(",")))
+
 
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
@@ -205,6 +208,8 @@ def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tens
               rowvec_ld: int = 0, algo_k: Optional[int] = None) -> None:
     """Launch tng_conv_gemm. groups: (view, a_c0, dw, dh, b_k0, nkb). weight: bf16 [Ncols, Ktot].
     algo_k: algorithmic reduction length (taps * Cin of the reference op) for the profiler's FLOP count."""
+    if "gemm" in _SKIP:
+        return
     lib = load()
     d = GemmDesc()
     require_cuda(weight, bias, rowvec, res, out_f32, out_bf16)
@@ -249,6 +254,8 @@ def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tens
 
 def attention(q, k, v, out, *, batch, heads, Lq, Lk, scale, q_col0=0, k_col0=0, v_col0=0, kbias=None, nsplit=1,
               q_lo_off=0, k_lo_off=0, v_lo_off=0, split_off=0) -> None:
+    if "attn" in _SKIP:
+        return
     lib = load()
     require_cuda(q, k, v, out, kbias)
     d = AttnDesc()
@@ -265,6 +272,8 @@ def attention(q, k, v, out, *, batch, heads, Lq, Lk, scale, q_col0=0, k_col0=0, 
 # --------------------------------------------------------------------------------------------------- norms etc.
 def groupnorm(x0, x1, NB, HW, groups, stats, gamma, beta, eps, act, y, *, split_off=0, raw=None, raw_split_off=0):
     """GroupNorm(+act) of the channel concat [x0 | x1] (x1 may be None) -> bf16 y; optional raw bf16 copy."""
+    if "gn" in _SKIP:
+        return
     lib = load()
     require_cuda(x0, x1, stats, gamma, beta, y, raw)
     C0 = x0.shape[-1]
@@ -279,6 +288,8 @@ def groupnorm(x0, x1, NB, HW, groups, stats, gamma, beta, eps, act, y, *, split_
 
 
 def layernorm(x, gamma, beta, eps, y, *, split_off=0):
+    if "ln" in _SKIP:
+        return
     require_cuda(x, gamma, beta, y)
     rows, Cc = x.shape
     check(load().tng_layernorm(x.data_ptr(), rows, Cc, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(),
