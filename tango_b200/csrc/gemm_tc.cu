@@ -59,9 +59,10 @@ struct GemmKernelParams {
   int dbg;       // TNG_GEMM_DBG: 1 = skip epilogue body, 2 = TMEM loads only (profiling experiments)
 };
 
-template <int BN>
+// PAIR: cta_group::2 — each CTA of the pair stages its own 128 A rows and only HALF of the weight tile
+template <int BN, bool PAIR = false>
 struct GemmCfg {
-  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // per epilogue warp: 32 x 32 fp32 swizzled transpose tile
   static constexpr int STAGES_RAW = (227 * 1024 - EPI_BYTES - 256) / STAGE_BYTES;
@@ -408,12 +409,20 @@ __device__ __forceinline__ void epi_tile_geglu(const GemmKernelParams& p, float*
   }
 }
 
-template <int BN>
+// CL = 1: single CTA. CL = 2: cluster of 2 along M with TMA multicast of the weight tile. CL = 3: CTA PAIR
+// (tcgen05 cta_group::2): one 256 x BN MMA spans both SMs, each SM stages its 128 A rows + half of B, so the operand
+// bytes each SM has to ingest per FLOP drop by ~28 % (the measured main-loop limiter); only the leader issues MMAs.
+// (original note) CL = thread-block-cluster size along M (1 or 2). With CL = 2 the two CTAs of a cluster work on adjacent M tiles of
+// the same N tile and share the weight tile: each loads half of B and TMA-multicasts it into both CTAs, halving the
+// L2 -> SM operand traffic for B (the main-loop bottleneck at N tile 160); smem slots are released by multicast commits.
+template <int BN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUtensorMap amap1,
                const __grid_constant__ CUtensorMap amap2, const __grid_constant__ CUtensorMap amap3,
                const __grid_constant__ CUtensorMap bmap, const __grid_constant__ GemmKernelParams p) {
-  using Cfg = GemmCfg<BN>;
+  constexpr bool PAIR = (CL == 3);
+  constexpr int CLUSTER = (CL == 1) ? 1 : 2;
+  using Cfg = GemmCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment (checked below)
   uint8_t* sA = smem;
@@ -438,31 +447,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     tma_prefetch_desc(&bmap);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL == 2 ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], EPI_WARPS);
+      mbar_init(&tempty_bar[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = (CLUSTER > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  if (CLUSTER > 1) cluster_sync_all();  // peer barriers are initialised before any multicast copy / commit targets them
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // work items: (pair of adjacent M tiles) x N tile; CTA `crank` of the cluster takes M tile 2*mp + crank
+  const int m_groups = (p.m_tiles + CLUSTER - 1) / CLUSTER;
+  const int total_tiles = m_groups * p.n_tiles;
+  const int work0 = blockIdx.x / CLUSTER, work_stride = gridDim.x / CLUSTER;
 
   if (warp == 0 && lane == 0) {
     // ===================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int tm = tile / p.n_tiles, tn = tile % p.n_tiles;
+    for (int tile = work0; tile < total_tiles; tile += work_stride) {
+      const int tm = (tile / p.n_tiles) * CLUSTER + crank, tn = tile % p.n_tiles;
       const int tw = tm % p.tiles_w;
       const int th = (tm / p.tiles_w) % p.tiles_h;
       const int tb = tm / (p.tiles_w * p.tiles_h);
@@ -472,20 +491,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
         const CUtensorMap* am = g.view == 0 ? &amap0 : g.view == 1 ? &amap1 : g.view == 2 ? &amap2 : &amap3;
         for (int kb = 0; kb < g.nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (PAIR) {
+            // both CTAs load into their own smem; all bytes are credited to the LEADER's full barrier
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_4d_2sm(sA + stage * A_TILE_BYTES, am, &full_bar[stage], g.a_c0 + kb * BK, w0 + g.dw, h0 + g.dh, n0);
+            tma_load_2d_2sm(sB + stage * Cfg::B_TILE_BYTES, &bmap, &full_bar[stage], g.b_k0 + kb * BK,
+                            tn * BN + crank * (BN / 2));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          if (p.dbg == 3) {  // experiment: A only (results are garbage)
+            mbar_arrive_expect_tx(&full_bar[stage], A_TILE_BYTES);
+            tma_load_4d(sA + stage * A_TILE_BYTES, am, &full_bar[stage], g.a_c0 + kb * BK, w0 + g.dw, h0 + g.dh, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_4d(sA + stage * A_TILE_BYTES, am, &full_bar[stage], g.a_c0 + kb * BK, w0 + g.dw, h0 + g.dh, n0);
-          tma_load_2d(sB + stage * Cfg::B_TILE_BYTES, &bmap, &full_bar[stage], g.b_k0 + kb * BK, tn * BN);
+          if (CL == 1) {
+            tma_load_2d(sB + stage * Cfg::B_TILE_BYTES, &bmap, &full_bar[stage], g.b_k0 + kb * BK, tn * BN);
+          } else {
+            // my half of the weight tile, written into BOTH CTAs (each CTA's full barrier sees A + both halves)
+            constexpr int HALF_ROWS = BN / 2;
+            tma_load_2d_mc(sB + stage * Cfg::B_TILE_BYTES + crank * HALF_ROWS * 128, &bmap, &full_bar[stage],
+                           g.b_k0 + kb * BK, tn * BN + crank * HALF_ROWS, static_cast<uint16_t>(3));
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================================================== MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+  } else if (warp == 1 && lane == 0 && (!PAIR || crank == 0)) {
+    // ===================================================== MMA issuer (pair mode: leader CTA only)
+    constexpr uint32_t idesc_full = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN, 0, 0);
+    constexpr uint32_t idesc_half = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN >= 128 ? 128 : BN, 0, 0);
+    const uint32_t idesc = (p.dbg == 4) ? idesc_half : idesc_full;  // dbg 4: N = 128 MMAs on the same loads
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = work0; tile < total_tiles; tile += work_stride, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -499,12 +542,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the (>>4) start-address field
-          umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          if (PAIR) umma_bf16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);
+        if (CL == 1) umma_commit(&empty_bar[stage]);
+        else if (CL == 2) umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>(3));  // frees the slot in both CTAs
+        else umma_commit2_mc(&empty_bar[stage], static_cast<uint16_t>(3));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tfull_bar[as]);
+      if (PAIR) umma_commit2_mc(&tfull_bar[as], static_cast<uint16_t>(3));  // each CTA drains its own 128 rows
+      else umma_commit(&tfull_bar[as]);
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue (8 warps)
@@ -515,8 +562,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     const int mode = (p.res ? 1 : 0) | (p.out_f32 ? 2 : 0) | (p.out_bf16 ? 4 : 0);
     const bool geglu = (p.act == TNG_ACT_GEGLU);
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int tm = tile / p.n_tiles, tn = tile % p.n_tiles;
+    for (int tile = work0; tile < total_tiles; tile += work_stride, ++it) {
+      const int tm = (tile / p.n_tiles) * CLUSTER + crank, tn = tile % p.n_tiles;
       const int tw = tm % p.tiles_w;
       const int th = (tm / p.tiles_w) % p.tiles_h;
       const int tb = tm / (p.tiles_w * p.tiles_h);
@@ -533,9 +580,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (static_cast<uint32_t>(ew * 32) << 16);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+      if (tm >= p.m_tiles) nvalid = 0;  // padding tile of an odd cluster tail
       const bool full = p.fast_epi && (nvalid == BM) && ((tn + 1) * BN <= p.Ncols);
       if (p.dbg == 1) {
         // experiment: no epilogue work at all
+      } else if (p.dbg == 3 || p.dbg == 4) {
+        // experiments on the main loop: no epilogue work
       } else if (p.dbg == 2) {
         for (int c = hf * 32; c < BN; c += 64) {
           uint32_t v[32];
@@ -574,36 +624,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       // all tcgen05.ld of this warp are complete (wait::ld): hand the accumulator stage back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (PAIR && crank != 0) mbar_arrive_remote(&tempty_bar[as], 0);  // the leader's MMA issuer owns the accumulators
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA until it is done too
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-template <int BN>
-static int launch_gemm(const CUtensorMap* am, const CUtensorMap& bm, const GemmKernelParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+template <int BN, int CL>
+static int launch_gemm_cl(const CUtensorMap* am, const CUtensorMap& bm, const GemmKernelParams& p, cudaStream_t st) {
+  constexpr int CLUSTER = (CL == 1) ? 1 : 2;
+  using Cfg = GemmCfg<BN, CL == 3>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return set_error(TNG_ECUDA, "cudaFuncSetAttribute(gemm_tc<%d>): %s", BN, cudaGetErrorString(e));
+    if (e != cudaSuccess) return set_error(TNG_ECUDA, "cudaFuncSetAttribute(gemm_tc<%d,%d>): %s", BN, CL, cudaGetErrorString(e));
     attr_set = true;
   }
-  const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(am[0], am[1], am[2], am[3], bm, p);
+  const int work = ((p.m_tiles + CLUSTER - 1) / CLUSTER) * p.n_tiles;
+  const int slots = num_sms() / CLUSTER;
+  const int grid = (work < slots ? work : slots) * CLUSTER;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, am[0], am[1], am[2], am[3], bm, p);
   count_launch();
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error(TNG_ECUDA, "gemm_tc<%d> launch: %s", BN, cudaGetErrorString(e));
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(TNG_ECUDA, "gemm_tc<%d,%d> launch: %s", BN, CL, cudaGetErrorString(e));
   return TNG_OK;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap* am, const CUtensorMap& bm, const GemmKernelParams& p, cudaStream_t st, int cl) {
+  if (cl == 3) return launch_gemm_cl<BN, 3>(am, bm, p, st);
+  return cl == 2 ? launch_gemm_cl<BN, 2>(am, bm, p, st) : launch_gemm_cl<BN, 1>(am, bm, p, st);
 }
 
 static bool is_pow2(long long x) { return x > 0 && (x & (x - 1)) == 0; }
@@ -703,6 +779,16 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   }
   if (d->act == TNG_ACT_GEGLU && !vec) return set_error(TNG_EINVAL, "GEGLU epilogue needs 16-byte aligned output");
 
+  // cluster of 2 CTAs along M sharing (multicasting) the weight tile: whenever there are at least two M tiles
+  // launch mode: 1 = single CTA, 2 = cluster-of-2 weight multicast, 3 = CTA pair (tcgen05 cta_group::2).
+  // TNG_GEMM_CLUSTER overrides the default for experiments.
+  int cl = 1;
+  {
+    static int force = -1;
+    if (force < 0) { const char* e = getenv("TNG_GEMM_CLUSTER"); force = e ? atoi(e) : 0; }
+    if (force >= 1 && force <= 3) cl = force;
+    if (p.m_tiles < 2 || bn_tile < 64) cl = 1;
+  }
   // tensor maps
   CUtensorMap am[4];
   for (int i = 0; i < 4; ++i) {
@@ -718,17 +804,17 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   {
     uint64_t dims[2] = {(uint64_t)d->Ktot, (uint64_t)d->Ncols};
     uint64_t strides[1] = {(uint64_t)(d->ldb > 0 ? d->ldb : d->Ktot) * 2};
-    uint32_t box[2] = {(uint32_t)BK, (uint32_t)bn_tile};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)(cl == 1 ? bn_tile : bn_tile / 2)};
     int rc = encode_tmap_bf16(&bm, d->b, 2, dims, strides, box);
     if (rc) return rc;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (bn_tile) {
-    case 32: return launch_gemm<32>(am, bm, p, st);
-    case 64: return launch_gemm<64>(am, bm, p, st);
-    case 128: return launch_gemm<128>(am, bm, p, st);
-    case 160: return launch_gemm<160>(am, bm, p, st);
-    case 256: return launch_gemm<256>(am, bm, p, st);
+    case 32: return launch_gemm<32>(am, bm, p, st, cl);
+    case 64: return launch_gemm<64>(am, bm, p, st, cl);
+    case 128: return launch_gemm<128>(am, bm, p, st, cl);
+    case 160: return launch_gemm<160>(am, bm, p, st, cl);
+    case 256: return launch_gemm<256>(am, bm, p, st, cl);
     default: return set_error(TNG_EINVAL, "block_n=%d unsupported", bn_tile);
   }
 }

@@ -154,3 +154,22 @@ def test_tango_generate_end_to_end_tiny(cuda):
     wref, _ = ohifi.decode_to_waveform(vsd, mel)
     got = t.vae._bufs.get("hwave_f", (1, wv.shape[1]), torch.float32)
     assert rel(got, wref) < 8e-2
+
+
+@pytest.mark.parametrize("precision", ["split"])
+def test_tiny_unet_long_clip_and_wide_text(cuda, precision):
+    """BASELINE configs 4/5 shapes on the tiny architecture: 30 s latent (768 x 16: partial M tiles at the lowest
+    level, 12 288-token self-attention) and a wider text encoder (cross_attention_dim 256, like the XL config's 2048)."""
+    cfg = dict(synth.TINY_UNET_CONFIG, cross_attention_dim=256)
+    sd = synth.synth_state_dict(synth.unet_param_shapes(cfg), seed=3)
+    g = torch.Generator().manual_seed(9)
+    sample = torch.randn(1, 8, 768, 16, generator=g)
+    ehs, mask = synth.synth_conditioning(1, 20, 256, seed=4, masked_tail=6)
+    ehs, mask = ehs[1:], mask[1:]
+    ref = ounet.unet_forward(sd, cfg, sample, torch.tensor(250), ehs, mask)
+    u = UNet2DConditionModel.from_config(cfg, precision=precision).to(cuda)
+    u.load_state_dict(sd)
+    out = u(sample.to(cuda), torch.tensor(250), ehs.to(cuda), encoder_attention_mask=mask.to(cuda)).sample
+    e = rel(out, ref)
+    print(f"tiny UNet 768x16 / text dim 256 {precision}: rel err vs oracle {e:.3e}")
+    assert e < TOL[precision]
