@@ -308,6 +308,11 @@ def run_ours(args):
     pk = peaks()
     m = t.model
     m.use_cuda_graph = False
+    m.inference(prompts, t.scheduler, 1, args.guidance, prompt_embeds=embeds_d, boolean_prompt_mask=mask_d, generator=gen)
+    torch.cuda.synchronize()
+    # Park the GPU behind a ~0.25 s spin kernel so that the (slow, Python-driven) eager launches queue up ahead of the
+    # GPU: the per-launch CUDA events then bracket pure kernel execution, not host launch latency.
+    torch.cuda._sleep(int(0.25 * 1.9e9))
     L.PROF.start()
     m.inference(prompts, t.scheduler, 2, args.guidance, prompt_embeds=embeds_d, boolean_prompt_mask=mask_d, generator=gen)
     prof = L.PROF.stop()
@@ -315,9 +320,13 @@ def run_ours(args):
     gm = prof.get("gemm_tc", {"launches": 1, "ms": 1.0, "flops": 0.0})
     at = prof.get("attention_tc", {"launches": 1, "ms": 1.0, "flops": 0.0})
     achieved = gm["flops"] / (gm["ms"] / 1e3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv/linear)",
             "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
             "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
             "launches_profiled": gm["launches"], "avg_launch_ms": gm["ms"] / max(1, gm["launches"]),
             "algorithmic_gflop_per_launch": gm["flops"] / max(1, gm["launches"]) / 1e9,

@@ -189,8 +189,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
         uint32_t v[32];
         tmem_ld32(ts + c, v);
         tmem_ld_wait();
+        // four independent max chains (a single serial chain of 128 dependent FMNMX costs ~4 cycles each)
+        float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
+        for (int i = 4; i < 32; i += 4) {
+          m0 = fmaxf(m0, __uint_as_float(v[i]));
+          m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+          m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+        }
+        m_tile = fmaxf(m_tile, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
       }
       m_tile *= sc;  // scale > 0
     } else {
@@ -238,11 +246,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       tmem_ld_wait();
       float pr[32];
       if (!tail) {
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;  // independent partial sums (ILP)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 32; i += 4) {
           pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -m_ref));
-          l_run += pr[i];
+          pr[i + 1] = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -m_ref));
+          pr[i + 2] = ex2_approx(fmaf(__uint_as_float(v[i + 2]), sc, -m_ref));
+          pr[i + 3] = ex2_approx(fmaf(__uint_as_float(v[i + 3]), sc, -m_ref));
+          l0 += pr[i]; l1 += pr[i + 1]; l2 += pr[i + 2]; l3 += pr[i + 3];
         }
+        l_run += (l0 + l1) + (l2 + l3);
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
