@@ -731,7 +731,12 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
     if (N <= 32) bn_tile = 32;
     else if (N <= 64) bn_tile = 64;
     else if (N % 256 == 0 && (long long)p.m_tiles * (N / 256) >= 2 * num_sms()) bn_tile = 256;
-    else if (N % 160 == 0) bn_tile = 160;
+    else if (N % 160 == 0) {
+      bn_tile = 160;
+      // under-filled launches (e.g. the 32x2 level of the UNet: 8 M tiles): more, smaller N tiles keep more SMs busy
+      if (N % 128 == 0 && (long long)p.m_tiles * (N / 160) * 2 <= num_sms() && (long long)p.m_tiles * (N / 128) <= num_sms())
+        bn_tile = 128;
+    }
     else if (N % 128 == 0) bn_tile = 128;
     else if (N % 64 == 0 && N < 256) bn_tile = 64;
     else bn_tile = 128;

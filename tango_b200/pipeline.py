@@ -220,7 +220,7 @@ class AudioDiffusion:
                      split_off=so)
 
         def run_unet():
-            unet.forward_rows(x_in, Bu, H, W, temb_cur, temb_cur.shape[1], out=model_out)
+            unet.forward_rows(x_in, Bu, H, W, temb_cur, temb_cur.shape[1], out=model_out, cfg_shared=cfg_on)
 
         graph = None
         per_forward = 0

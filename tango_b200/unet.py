@@ -292,23 +292,35 @@ class UNet2DConditionModel:
         run_conv(r.conv2, a2, NB, H, W, sc_x=raw, res=None if has_sc else x0, out_f32=out)
         return out
 
-    def _transformer(self, name, t, x, NB, H, W, kv, bias, Lk):
-        R, HW, s, sp, Cc = NB * H * W, H * W, self.s, self.split, t.C
+    def _transformer(self, name, t, x, NB, H, W, kv, bias, Lk, shared_half: bool = False):
+        """shared_half: `x` holds only the first NB/2 images and stands for both CFG halves (identical latents and
+        timestep): everything up to the self-attention output is computed once and duplicated before the
+        cross-attention, the first place where the two halves see different data."""
+        HW, s, sp, Cc = H * W, self.s, self.split, t.C
         so = Cc if sp else 0
-        a = self._buf("a", (R, Cc * s), torch.bfloat16)
-        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
-        L.groupnorm(x, None, NB, HW, 32, stats, t.nw, t.nb, 1e-6, L.ACT_NONE, a, split_off=so)
-        hs = self._buf("hs", (R, Cc), torch.float32)
-        run_linear(t.proj_in, a, out_f32=hs)
-        n = self._buf("ln", (R, Cc * s), torch.bfloat16)
-        L.layernorm(hs, t.ln1w, t.ln1b, 1e-5, n, split_off=so)
-        qkv = self._buf("qkv", (R, 3 * Cc * s), torch.bfloat16)
-        run_linear(t.qkv, n, out_bf16=qkv)
-        ao = self._buf("ao", (R, Cc * s), torch.bfloat16)
+        NBp = NB // 2 if shared_half else NB   # batch of the (possibly shared) prefix
+        Rp, R = NBp * HW, NB * HW
         scale = 64 ** -0.5
-        L.attention(qkv, qkv, qkv, ao, batch=NB, heads=t.heads, Lq=HW, Lk=HW, scale=scale, q_col0=0, k_col0=Cc,
-                    v_col0=2 * Cc, nsplit=s, q_lo_off=3 * Cc, k_lo_off=3 * Cc, v_lo_off=3 * Cc, split_off=so)
-        run_linear(t.out1, ao, res=hs, out_f32=hs)
+        a = self._buf("a", (Rp, Cc * s), torch.bfloat16)
+        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
+        L.groupnorm(x, None, NBp, HW, 32, stats, t.nw, t.nb, 1e-6, L.ACT_NONE, a, split_off=so)
+        hs = self._buf("hs", (R, Cc), torch.float32)
+        hsp = hs[:Rp]
+        run_linear(t.proj_in, a, out_f32=hsp)
+        n = self._buf("ln", (R, Cc * s), torch.bfloat16)
+        L.layernorm(hsp, t.ln1w, t.ln1b, 1e-5, n[:Rp], split_off=so)
+        qkv = self._buf("qkv", (R, 3 * Cc * s), torch.bfloat16)
+        run_linear(t.qkv, n[:Rp], out_bf16=qkv[:Rp])
+        ao = self._buf("ao", (R, Cc * s), torch.bfloat16)
+        L.attention(qkv[:Rp], qkv[:Rp], qkv[:Rp], ao[:Rp], batch=NBp, heads=t.heads, Lq=HW, Lk=HW, scale=scale, q_col0=0,
+                    k_col0=Cc, v_col0=2 * Cc, nsplit=s, q_lo_off=3 * Cc, k_lo_off=3 * Cc, v_lo_off=3 * Cc, split_off=so)
+        run_linear(t.out1, ao[:Rp], res=hsp, out_f32=hsp)
+        if shared_half:
+            hs[Rp:].copy_(hsp)          # second CFG half = first half up to here
+            xf = self._buf(name + "_xdup", (R, Cc), torch.float32)
+            xf[:Rp].copy_(x)
+            xf[Rp:].copy_(x)
+            x = xf
         L.layernorm(hs, t.ln2w, t.ln2b, 1e-5, n, split_off=so)
         q = self._buf("q2", (R, Cc * s), torch.bfloat16)
         run_linear(t.q2, n, out_bf16=q)
@@ -325,10 +337,13 @@ class UNet2DConditionModel:
         return out
 
     def forward_rows(self, x_in: torch.Tensor, NB: int, H: int, W: int, temb: torch.Tensor, temb_ld: int,
-                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     out: Optional[torch.Tensor] = None, cfg_shared: bool = False) -> torch.Tensor:
         """The UNet on channels-last rows. x_in: bf16 [NB*H*W, in_ch * s] (hi | lo in split mode);
         temb: fp32 [NB, >= temb_total] rows of time_embedding_table (row stride temb_ld). Returns fp32 [NB*H*W, out_ch].
-        set_conditioning() must have been called for this batch."""
+        set_conditioning() must have been called for this batch.
+        cfg_shared: the two halves of the batch carry identical latents and timesteps (classifier-free guidance,
+        models.py:235): conv_in, the first resnet and the first transformer up to its self-attention output — everything
+        before the first cross-attention — are then computed for one half only and duplicated."""
         self._pack()
         P, cfg, s, sp = self.P, self.config, self.s, self.split
         c = self._cond
@@ -338,13 +353,24 @@ class UNet2DConditionModel:
         if H % (1 << (nlev - 1)) or W % (1 << (nlev - 1)):
             raise L.TangoB200Error(f"latent size {H}x{W} must be divisible by {1 << (nlev - 1)}")
         R = NB * H * W
+        shared = bool(cfg_shared) and NB % 2 == 0 and bool(P["down"][0].attns)
+        NBp = NB // 2 if shared else NB
         h = self._buf("conv_in", (R, P["conv_in"].cout), torch.float32)
-        run_conv(P["conv_in"], x_in, NB, H, W, out_f32=h)
+        run_conv(P["conv_in"], x_in, NBp, H, W, out_f32=h[:NBp * H * W])
+        if shared:
+            h[NBp * H * W:].copy_(h[:NBp * H * W])   # the conv_in output is also a skip connection (full batch)
         skips = [h]
         ti = 0
         ch, cw = H, W
         for i, blk in enumerate(P["down"]):
             for j, r in enumerate(blk.resnets):
+                first = shared and i == 0 and j == 0
+                if first:
+                    hp = self._resnet("d0r0", r, h[:NBp * H * W], None, NBp, ch, cw, temb, temb_ld)
+                    h = self._transformer("d0t0", blk.attns[0], hp, NB, ch, cw, c.kvs[ti], c.bias, c.Lk, shared_half=True)
+                    ti += 1
+                    skips.append(h)
+                    continue
                 h = self._resnet(f"d{i}r{j}", r, h, None, NB, ch, cw, temb, temb_ld)
                 if blk.attns:
                     h = self._transformer(f"d{i}t{j}", blk.attns[j], h, NB, ch, cw, c.kvs[ti], c.bias, c.Lk)
