@@ -204,9 +204,10 @@ def run_reference(args):
 
 
 def workload_config(args, world):
-    return {"workload": "Tango base UNet (configs/diffusion_model_config.json), batch %d prompts/GPU x %d GPU, %d %s steps, "
-                        "CFG %.1f, 10.24 s clips, 64 synthetic T5 tokens, + VAE decoder + HiFi-GAN -> int16 16 kHz"
-                        % (args.batch, world, args.denoise_steps, args.scheduler.upper(), args.guidance),
+    return {"workload": "Tango " + args.unet + " UNet, batch %d prompts/GPU x %d GPU, %d %s steps, "
+                        "CFG %.1f, %.2f s clips, 64 synthetic T5 tokens, + VAE decoder + HiFi-GAN -> int16 16 kHz"
+                        % (args.batch, world, args.denoise_steps, args.scheduler.upper(), args.guidance,
+                           (4 * args.latent_h * 160 + 32) / 16000.0),
             "global_batch": args.batch * world, "unet_batch_per_gpu": 2 * args.batch, "denoise_steps": args.denoise_steps,
             "scheduler": args.scheduler, "guidance": args.guidance, "precision": args.precision,
             "parallelism": f"prompt-shard x{world}", "l2": "working set (1.7 GB bf16 weights + activations) >> 126 MB L2"}
@@ -231,8 +232,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.set_grad_enabled(False)
 
-    cfg = synth.BASE_UNET_CONFIG
+    cfg = synth.BASE_UNET_CONFIG if args.unet == "base" else synth.XL_UNET_CONFIG
     B = args.batch
+    latent_shape = (args.latent_h, 16)
+    audio_s = (4 * args.latent_h * 160 + 32) / 16000.0   # HiFi-GAN: 160 samples per mel frame (+32 tail)
     t = Tango.from_synthetic(unet_config=cfg, device=dev, precision=args.precision, scheduler=args.scheduler)
     if world > 1:
         # one-time NCCL broadcast of the (rank-0) weights over NVLink, as a sharded deployment would do at load
@@ -246,7 +249,7 @@ def run_ours(args):
 
     def one_pass_device():
         lat = t.model.inference(prompts, t.scheduler, args.denoise_steps, args.guidance, prompt_embeds=embeds_d,
-                                boolean_prompt_mask=mask_d, generator=gen)
+                                boolean_prompt_mask=mask_d, generator=gen, latent_shape=latent_shape)
         B_, Cl, H, W = lat.shape
         rows = lat.permute(0, 2, 3, 1).reshape(B_ * H * W, Cl).contiguous()
         mel = t.vae.decode_rows(rows, B_, H, W)
@@ -254,7 +257,8 @@ def run_ours(args):
 
     def one_pass_e2e():
         return t.generate_for_batch(prompts, steps=args.denoise_steps, guidance=args.guidance, batch_size=B,
-                                    prompt_embeds=embeds_pin, boolean_prompt_mask=mask_pin, generator=gen)
+                                    prompt_embeds=embeds_pin, boolean_prompt_mask=mask_pin, generator=gen,
+                                    latent_shape=latent_shape)
 
     def barrier():
         if world > 1:
@@ -285,7 +289,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     launches = (L.launch_count() - n0) + graph_launches
     dev_ms = parallel.max_over_ranks(dev_ms, dev)
-    value = world * B * AUDIO_S_PER_SAMPLE * args.steps / (dev_ms / 1e3)
+    value = world * B * audio_s * args.steps / (dev_ms / 1e3)
 
     # ---------------- timed: end to end through the public API with host buffers
     one_pass_e2e()
@@ -295,7 +299,7 @@ def run_ours(args):
         waves = one_pass_e2e()
     barrier()
     e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, dev)
-    e2e_value = world * B * AUDIO_S_PER_SAMPLE * args.steps / e2e_s
+    e2e_value = world * B * audio_s * args.steps / e2e_s
     h2d = embeds_pin.numel() * 4 + mask_pin.numel()
     d2h = sum(int(w.nbytes) for w in waves)
 
@@ -308,13 +312,15 @@ def run_ours(args):
     pk = peaks()
     m = t.model
     m.use_cuda_graph = False
-    m.inference(prompts, t.scheduler, 1, args.guidance, prompt_embeds=embeds_d, boolean_prompt_mask=mask_d, generator=gen)
+    m.inference(prompts, t.scheduler, 1, args.guidance, prompt_embeds=embeds_d, boolean_prompt_mask=mask_d, generator=gen,
+                latent_shape=latent_shape)
     torch.cuda.synchronize()
     # Park the GPU behind a ~0.25 s spin kernel so that the (slow, Python-driven) eager launches queue up ahead of the
     # GPU: the per-launch CUDA events then bracket pure kernel execution, not host launch latency.
     torch.cuda._sleep(int(0.25 * 1.9e9))
     L.PROF.start()
-    m.inference(prompts, t.scheduler, 2, args.guidance, prompt_embeds=embeds_d, boolean_prompt_mask=mask_d, generator=gen)
+    m.inference(prompts, t.scheduler, 2, args.guidance, prompt_embeds=embeds_d, boolean_prompt_mask=mask_d, generator=gen,
+                latent_shape=latent_shape)
     prof = L.PROF.stop()
     m.use_cuda_graph = True
     gm = prof.get("gemm_tc", {"launches": 1, "ms": 1.0, "flops": 0.0})
@@ -332,7 +338,11 @@ def run_ours(args):
             "algorithmic_gflop_per_launch": gm["flops"] / max(1, gm["launches"]) / 1e9,
             "attention_tc": {"achieved": at["flops"] / (at["ms"] / 1e3) / 1e12, "launches": at["launches"],
                              "avg_launch_ms": at["ms"] / max(1, at["launches"])}}
-    f_total = B * (2 * args.denoise_steps * F_UNET + F_VAE + F_VOC)
+    if args.latent_h == 256:
+        f_unet, f_vae, f_voc = (F_UNET if args.unet == "base" else 806.453e9), F_VAE, F_VOC
+    else:  # SURVEY.md §8d figures for the 30 s extension (768 x 16); other lengths are not tabulated
+        f_unet, f_vae, f_voc = (3137.856e9 if args.unet == "base" else 3141.13e9), 2217.564e9, 3080.714e9
+    f_total = B * (2 * args.denoise_steps * f_unet + f_vae + f_voc)
     whole = f_total * args.steps / (dev_ms / 1e3) / 1e12
     roof["whole_path_tflops"] = whole
     roof["whole_path_frac"] = whole / pk["bf16_tflops_sustained"]
@@ -377,6 +387,8 @@ def main():
     ap.add_argument("--scheduler", default="ddim", choices=["ddim", "ddpm"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "split"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latent-h", type=int, default=256, help="latent time frames: 256 = 10.24 s (reference), 768 = 30.7 s")
+    ap.add_argument("--unet", default="base", choices=["base", "xl"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

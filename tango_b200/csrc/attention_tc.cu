@@ -42,7 +42,7 @@ struct AttnCfg {
   static constexpr int Q_BYTES = NSPLIT * AT_CHUNK;
   static constexpr int KV_BYTES = NSPLIT * AT_CHUNK;      // each of K and V per buffer
   static constexpr int P_BYTES = NSPLIT * 2 * AT_CHUNK;   // [128][128] hi (+ lo)
-  static constexpr int SMEM_BYTES = Q_BYTES + AT_NBUF * 2 * KV_BYTES + P_BYTES + 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + AT_NBUF * 2 * KV_BYTES + P_BYTES + 128 + AT_BN * 4;  // + key-bias row
   static constexpr int TMEM_COLS = 256;                   // S: 128, O: 64
 };
 
@@ -62,6 +62,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   uint64_t* bar_s = bars + 1 + AT_NBUF;  // [1]  S_j ready (and P V_{j-1} drained)
   uint64_t* bar_o = bars + 2 + AT_NBUF;  // [1]  final P V drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + AT_NBUF);
+  float* sbias = reinterpret_cast<float*>(sP + Cfg::P_BYTES + 128);  // per-tile key bias (log2 domain), -inf = masked
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -129,7 +130,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
     umma_commit(bar_s);
   };
   // O (+)= P V_tile   (A = P K-major chunks, B = V MN-major: 16 keys per MMA = 2 swizzle atoms = 2048 B)
-  auto issue_pv = [&](int tile, uint32_t accumulate) {
+  auto issue_pv = [&](int tile, uint32_t accumulate, int nk16) {
     const int buf = tile % AT_NBUF;
     constexpr uint32_t idesc = umma_idesc_bf16(AT_BM, AT_D, 0, 1);
     const uint32_t pa = smem_u32(sP), va = smem_u32(sV + buf * Cfg::KV_BYTES);
@@ -140,6 +141,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
     for (int t = 0; t < NT; ++t) {
 #pragma unroll
       for (int k = 0; k < AT_BN / 16; ++k) {
+        if (k >= nk16) break;  // keys beyond the written P columns (short last tile)
         const uint64_t adesc =
             umma_desc_sw128(pa + psel[t] * 2 * AT_CHUNK + (k >> 2) * AT_CHUNK, 16, 1024) + 2 * (k & 3);
         const uint64_t bdesc = umma_desc_sw128(va + vsel[t] * AT_CHUNK + k * 2048, 1024, 1024);
@@ -181,6 +183,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
     if (tid == 0 && j >= 1 && j + 1 < n_tiles) load_kv(j + 1);
     const int kv0 = j * AT_BN;
     const bool tail = (kb != nullptr) || (kv0 + AT_BN > p.Lk);
+    // columns actually processed in this tile (multiple of 32); P columns beyond are never written nor multiplied
+    const int ncols = tail ? min(AT_BN, ((p.Lk - kv0) + 31) & ~31) : AT_BN;
+    if (tail) {
+      // one bias value per key of the tile, shared through smem: additive mask bias (already * log2e) or -inf
+      // for keys beyond Lk -> the softmax passes below need no per-element predicates or global loads
+      const int kv = kv0 + tid;
+      float bv = -INFINITY;
+      if (kv < p.Lk) bv = kb ? kb[kv] * LOG2E : 0.f;
+      __syncthreads();  // previous tile's readers are done
+      sbias[tid] = bv;
+      __syncthreads();
+    }
     // ---- pass 1: row maximum (log2 domain)
     float m_tile = -INFINITY;
     if (!tail) {
@@ -203,19 +217,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       m_tile *= sc;  // scale > 0
     } else {
 #pragma unroll 1
-      for (int c = 0; c < AT_BN; c += 32) {
+      for (int c = 0; c < ncols; c += 32) {
         uint32_t v[32];
         tmem_ld32(ts + c, v);
         tmem_ld_wait();
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kv = kv0 + c + i;
-          if (kv < p.Lk) {
-            float s = __uint_as_float(v[i]) * sc;
-            if (kb) s += kb[kv] * LOG2E;
-            m_tile = fmaxf(m_tile, s);
-          }
+        for (int i = 0; i < 32; i += 4) {
+          m0 = fmaxf(m0, fmaf(__uint_as_float(v[i]), sc, sbias[c + i]));
+          m1 = fmaxf(m1, fmaf(__uint_as_float(v[i + 1]), sc, sbias[c + i + 1]));
+          m2 = fmaxf(m2, fmaf(__uint_as_float(v[i + 2]), sc, sbias[c + i + 2]));
+          m3 = fmaxf(m3, fmaf(__uint_as_float(v[i + 3]), sc, sbias[c + i + 3]));
         }
+        m_tile = fmaxf(m_tile, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
       }
     }
     // ---- lazy rescale of the running state (warp-uniform decision; tcgen05.ld/st are warp collectives)
@@ -240,7 +254,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
     }
     // ---- pass 2: probabilities -> bf16 (hi/lo) -> swizzled smem
 #pragma unroll 1
-    for (int c = 0; c < AT_BN; c += 32) {
+    for (int c = 0; c < ncols; c += 32) {
       uint32_t v[32];
       tmem_ld32(ts + c, v);
       tmem_ld_wait();
@@ -257,14 +271,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
         }
         l_run += (l0 + l1) + (l2 + l3);
       } else {
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kv = kv0 + c + i;
-          float s = __uint_as_float(v[i]) * sc;
-          if (kb && kv < p.Lk) s += kb[kv] * LOG2E;
-          pr[i] = (kv < p.Lk) ? ex2_approx(s - m_ref) : 0.f;
-          l_run += pr[i];
+        for (int i = 0; i < 32; i += 4) {
+          pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sc, sbias[c + i]) - m_ref);       // ex2(-inf) = 0 for masked keys
+          pr[i + 1] = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, sbias[c + i + 1]) - m_ref);
+          pr[i + 2] = ex2_approx(fmaf(__uint_as_float(v[i + 2]), sc, sbias[c + i + 2]) - m_ref);
+          pr[i + 3] = ex2_approx(fmaf(__uint_as_float(v[i + 3]), sc, sbias[c + i + 3]) - m_ref);
+          l0 += pr[i]; l1 += pr[i + 1]; l2 += pr[i + 2]; l3 += pr[i + 3];
         }
+        l_run += (l0 + l1) + (l2 + l3);
       }
       uint8_t* prow = prow_base + (c >> 6) * AT_CHUNK;
       const int u0 = (c & 63) >> 3;  // first 16-byte unit inside the 128-byte row
@@ -293,7 +309,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      issue_pv(j, j > 0 ? 1u : 0u);
+      issue_pv(j, j > 0 ? 1u : 0u, ncols / 16);
       if (j + 1 < n_tiles) {
         mbar_wait(&bar_kv[(j + 1) % AT_NBUF], ((j + 1) / AT_NBUF) & 1);
         tc_fence_after();
