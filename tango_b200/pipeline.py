@@ -81,6 +81,7 @@ class AudioDiffusion:
         self.tokenizer = None
         self.text_encoder = None
         self._state = {}
+        self._temb_cache = {}
         self.last_step_ms: Optional[float] = None
         self.last_kernel_launches = 0
         self.launches_per_forward = 0
@@ -199,7 +200,10 @@ class AudioDiffusion:
 
         unet = self.unet
         unet.set_conditioning(prompt_embeds, boolean_prompt_mask)
-        temb_table = unet.time_embedding_table(timesteps)            # [steps, temb_total]
+        tkey = (id(unet.P),) + tuple(sch._t_list)   # unet.P is rebuilt when weights are (re)loaded
+        if self._temb_cache.get("key") != tkey:   # batch- and data-independent: reuse across calls with the same grid
+            self._temb_cache = {"key": tkey, "table": unet.time_embedding_table(timesteps)}
+        temb_table = self._temb_cache["table"]                      # [steps, temb_total]
         coef = sch.coefficient_table(device)                          # [steps, 10]
         s = unet.s
         HW = H * W

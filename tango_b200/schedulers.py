@@ -88,9 +88,12 @@ class _SchedulerBase:
         return (np.arange(0, n) * ratio).round()[::-1].copy().astype(np.int64)
 
     def _finish_set_timesteps(self, device):
-        rows = [self._coefficients(int(t)) for t in self.timesteps.tolist()]
-        self._coef_host = torch.stack(rows).contiguous()
         self._t_list = [int(t) for t in self.timesteps.tolist()]
+        key = tuple(self._t_list)
+        cache = self.__dict__.setdefault("_table_cache", {})
+        if key not in cache:   # ~40 tiny fp32 torch ops per step: computed once per grid, reused by later calls
+            cache[key] = torch.stack([self._coefficients(t) for t in self._t_list]).contiguous()
+        self._coef_host = cache[key]
         self._t_index = {t: i for i, t in enumerate(self._t_list)}
         self._coef_dev = None
         if device is not None:
