@@ -17,6 +17,7 @@
 // hi*hi + lo*hi + hi*lo, which restores ~fp32 accuracy on the bf16 tensor cores (1 CTA / SM).
 #include "tng_ptx.cuh"
 #include "tng_internal.h"
+#include <stdlib.h>
 
 namespace tng {
 
@@ -362,6 +363,317 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   }
 }
 
+
+// =====================================================================================================================
+// attention_ws_kernel — warp-specialised variant (perf mode, NSPLIT = 1): 8 softmax warps + 1 loader/issuer warp, one
+// CTA per SM. Two threads share a query row (warps w and w+4 own the two 64-key halves of the 128-key tile), S is
+// double-buffered in TMEM and the issuer keeps the tensor pipe one tile ahead:
+//     issue order:  ... P V_{j-1}, Q K_{j+1}^T, P V_j, Q K_{j+2}^T ...   (each pair as soon as P_j is in smem)
+// so Q K^T of the next tile and P V of the previous one execute while the softmax warps work on the current tile.
+// No __syncthreads in the main loop: softmax -> issuer through an mbarrier with 256 arrivals, issuer -> softmax through
+// tcgen05.commit barriers; the two threads of a row exchange their partial row max through smem + a 64-thread named
+// barrier.
+constexpr int AW_NBUF = 3;
+constexpr int AW_SOFTMAX_THREADS = 256;
+constexpr int AW_THREADS = AW_SOFTMAX_THREADS + 32;
+constexpr int AW_SMEM_BYTES = AT_CHUNK /*Q*/ + AW_NBUF * 2 * AT_CHUNK /*K,V*/ + 2 * AT_CHUNK /*P*/ + 128 /*barriers*/ +
+                              AT_BN * 4 /*bias*/ + 2 * 2 * AT_BM * 4 /*row exchange*/;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(AW_THREADS, 1)
+attention_ws_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                    const __grid_constant__ CUtensorMap vmap, const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + AT_CHUNK;               // [NBUF][16 KB]
+  uint8_t* sV = sK + AW_NBUF * AT_CHUNK;     // [NBUF][16 KB]
+  uint8_t* sP = sV + AW_NBUF * AT_CHUNK;     // 2 chunks of 64 keys
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_CHUNK);
+  uint64_t* bar_q = bars;                   // [1]
+  uint64_t* bar_kv = bars + 1;              // [NBUF]
+  uint64_t* bar_s = bars + 1 + AW_NBUF;     // [2]  S buffer ready
+  uint64_t* bar_pv = bars + 3 + AW_NBUF;    // [1]  P V_j drained (P smem / O / K-V buffer reusable)
+  uint64_t* bar_p = bars + 4 + AW_NBUF;     // [1]  P_j written + S_j consumed (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + AW_NBUF);
+  float* sbias = reinterpret_cast<float*>(sP + 2 * AT_CHUNK + 128);
+  float* xch = sbias + AT_BN;               // [2 (tile parity)][2 (half)][128 rows]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int q0 = blockIdx.x * AT_BM;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_tiles = (p.Lk + AT_BN - 1) / AT_BN;
+
+  if (tid == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("[tng] attention_ws: dynamic smem base not 1024-byte aligned\n");
+      __trap();
+    }
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < AW_NBUF; ++i) mbar_init(&bar_kv[i], 1);
+    mbar_init(&bar_s[0], 1);
+    mbar_init(&bar_s[1], 1);
+    mbar_init(bar_pv, 1);
+    mbar_init(bar_p, AW_SOFTMAX_THREADS);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_o = tmem_base + 256;
+
+  if (warp == 8) {
+    // ================================================================= loader + MMA issuer (one thread)
+    if (lane == 0) {
+      tma_prefetch_desc(&qmap);
+      tma_prefetch_desc(&kmap);
+      tma_prefetch_desc(&vmap);
+      auto load_kv = [&](int tile) {
+        const int buf = tile % AW_NBUF;
+        mbar_arrive_expect_tx(&bar_kv[buf], 2 * AT_CHUNK);
+        tma_load_3d(sK + buf * AT_CHUNK, &kmap, &bar_kv[buf], p.k_col0 + head * AT_D, tile * AT_BN, b);
+        tma_load_3d(sV + buf * AT_CHUNK, &vmap, &bar_kv[buf], p.v_col0 + head * AT_D, tile * AT_BN, b);
+      };
+      auto issue_qk = [&](int tile) {
+        constexpr uint32_t idesc = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
+        const uint64_t adesc = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(sK + (tile % AW_NBUF) * AT_CHUNK), 16, 1024);
+        const uint32_t d = tmem_base + (tile & 1) * 128;
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0 ? 1u : 0u);
+        umma_commit(&bar_s[tile & 1]);
+      };
+      auto issue_pv = [&](int tile, int nk16) {
+        constexpr uint32_t idesc = umma_idesc_bf16(AT_BM, AT_D, 0, 1);
+        const uint32_t pa = smem_u32(sP), va = smem_u32(sV + (tile % AW_NBUF) * AT_CHUNK);
+        for (int k = 0; k < nk16; ++k) {
+          const uint64_t adesc = umma_desc_sw128(pa + (k >> 2) * AT_CHUNK, 16, 1024) + 2 * (k & 3);
+          const uint64_t bdesc = umma_desc_sw128(va + k * 2048, 1024, 1024);
+          umma_bf16(tm_o, adesc, bdesc, idesc, (tile > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_pv);
+      };
+      mbar_arrive_expect_tx(bar_q, AT_CHUNK);
+      tma_load_3d(sQ, &qmap, bar_q, p.q_col0 + head * AT_D, q0, b);
+      for (int t = 0; t < AW_NBUF && t < n_tiles; ++t) load_kv(t);
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_kv[0], 0);
+      tc_fence_after();
+      issue_qk(0);
+      if (n_tiles > 1) {
+        mbar_wait(&bar_kv[1], 0);
+        tc_fence_after();
+        issue_qk(1);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(bar_p, j & 1);  // P_j in smem, S_j fully read, O rescaled if needed
+        tc_fence_after();
+        const int kv0 = j * AT_BN;
+        const bool tail = (p.kbias != nullptr) || (kv0 + AT_BN > p.Lk);
+        const int ncols = tail ? min(AT_BN, ((p.Lk - kv0) + 31) & ~31) : AT_BN;
+        issue_pv(j, ncols / 16);
+        if (j + 2 < n_tiles) {
+          mbar_wait(&bar_kv[(j + 2) % AW_NBUF], ((j + 2) / AW_NBUF) & 1);
+          tc_fence_after();
+          issue_qk(j + 2);       // into the S buffer tile j just released
+        }
+        if (j + AW_NBUF < n_tiles) {
+          mbar_wait(bar_pv, j & 1);  // P V_j (and Q K_j^T long before) drained: K/V buffer j % NBUF is free
+          load_kv(j + AW_NBUF);
+        }
+      }
+    }
+  } else {
+    // ================================================================= softmax warps (two threads per query row)
+    const int quarter = warp & 3;
+    const int hf = warp >> 2;                 // which 64-key half of the tile this thread owns
+    const int r = quarter * 32 + lane;        // query row == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t to = tm_o + lane_addr + 32 * hf;   // my 32 of the 64 O columns
+    float m_ref = -INFINITY, l_run = 0.f;
+    const float sc = p.scale_log2e;
+    const float* kb = p.kbias ? p.kbias + static_cast<long long>(b) * p.Lk : nullptr;
+    constexpr float LOG2E = 1.4426950408889634f;
+    uint8_t* prow = sP + hf * AT_CHUNK + r * 128;
+    const int rsw = r & 7;
+    const int c0 = 64 * hf;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int kv0 = j * AT_BN;
+      const bool tail = (kb != nullptr) || (kv0 + AT_BN > p.Lk);
+      const int ncols = tail ? min(AT_BN, ((p.Lk - kv0) + 31) & ~31) : AT_BN;
+      const int cend = min(c0 + 64, ncols);
+      if (tail) {
+        named_bar_sync(5, AW_SOFTMAX_THREADS);     // previous tile's readers of sbias are done
+        if (tid < AT_BN) {
+          const int kv = kv0 + tid;
+          float bv = -INFINITY;
+          if (kv < p.Lk) bv = kb ? kb[kv] * LOG2E : 0.f;
+          sbias[tid] = bv;
+        }
+        named_bar_sync(5, AW_SOFTMAX_THREADS);
+      }
+      __syncwarp();
+      mbar_wait(&bar_s[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ts = tmem_base + (j & 1) * 128 + lane_addr;
+      // ---- pass 1: partial row maximum over my key half (log2 domain)
+      float m_part = -INFINITY;
+#pragma unroll 1
+      for (int c = c0; c < cend; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(ts + c, v);
+        tmem_ld_wait();
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        if (!tail) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(v[i]));
+            m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+            m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+          }
+          m_part = fmaxf(m_part, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sc);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmaxf(m0, fmaf(__uint_as_float(v[i]), sc, sbias[c + i]));
+            m1 = fmaxf(m1, fmaf(__uint_as_float(v[i + 1]), sc, sbias[c + i + 1]));
+            m2 = fmaxf(m2, fmaf(__uint_as_float(v[i + 2]), sc, sbias[c + i + 2]));
+            m3 = fmaxf(m3, fmaf(__uint_as_float(v[i + 3]), sc, sbias[c + i + 3]));
+          }
+          m_part = fmaxf(m_part, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+        }
+      }
+      // ---- exchange with the thread that owns the other half of this row
+      float* xr = xch + (j & 1) * (2 * AT_BM);
+      xr[hf * AT_BM + r] = m_part;
+      named_bar_sync(1 + quarter, 64);
+      const float m_tile = fmaxf(m_part, xr[(hf ^ 1) * AT_BM + r]);
+      // P smem and O are touched below: P V_{j-1} must have drained
+      if (j > 0) {
+        mbar_wait(bar_pv, (j - 1) & 1);
+        tc_fence_after();
+      }
+      // ---- lazy rescale (identical decision in both threads of a row; warp-uniform execution of tcgen05.ld/st)
+      const bool need = m_tile > m_ref + AT_LAZY;
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = need ? m_tile : m_ref;
+        const float f = (j == 0) ? 0.f : ex2_approx(m_ref - m_new);
+        l_run *= f;
+        if (j > 0) {
+          uint32_t v[32];
+          tmem_ld32(to, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+          tmem_st32(to, v);
+          tmem_st_wait();
+        }
+        m_ref = m_new;
+      }
+      // ---- pass 2: probabilities of my key half -> bf16 -> swizzled smem (A operand of P V)
+#pragma unroll 1
+      for (int c = c0; c < cend; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(ts + c, v);
+        tmem_ld_wait();
+        float pr[32];
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        if (!tail) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -m_ref));
+            pr[i + 1] = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -m_ref));
+            pr[i + 2] = ex2_approx(fmaf(__uint_as_float(v[i + 2]), sc, -m_ref));
+            pr[i + 3] = ex2_approx(fmaf(__uint_as_float(v[i + 3]), sc, -m_ref));
+            l0 += pr[i]; l1 += pr[i + 1]; l2 += pr[i + 2]; l3 += pr[i + 3];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sc, sbias[c + i]) - m_ref);
+            pr[i + 1] = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, sbias[c + i + 1]) - m_ref);
+            pr[i + 2] = ex2_approx(fmaf(__uint_as_float(v[i + 2]), sc, sbias[c + i + 2]) - m_ref);
+            pr[i + 3] = ex2_approx(fmaf(__uint_as_float(v[i + 3]), sc, sbias[c + i + 3]) - m_ref);
+            l0 += pr[i]; l1 += pr[i + 1]; l2 += pr[i + 2]; l3 += pr[i + 3];
+          }
+        }
+        l_run += (l0 + l1) + (l2 + l3);
+        const int u0 = ((c - c0) >> 3);  // first 16-byte unit inside my 128-byte P row (0 or 4)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w;
+          w.x = pack_bf16(pr[8 * u + 0], pr[8 * u + 1]);
+          w.y = pack_bf16(pr[8 * u + 2], pr[8 * u + 3]);
+          w.z = pack_bf16(pr[8 * u + 4], pr[8 * u + 5]);
+          w.w = pack_bf16(pr[8 * u + 6], pr[8 * u + 7]);
+          *reinterpret_cast<uint4*>(prow + (((u0 + u) ^ rsw) << 4)) = w;
+        }
+      }
+      // P (generic-proxy writes) -> async proxy; S reads / O rescale complete -> tell the issuer
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+
+    // ---- finalize: O / l -> bf16; the two threads of a row each write 32 of the 64 head columns
+    mbar_wait(bar_pv, (n_tiles - 1) & 1);
+    tc_fence_after();
+    float* xr = xch + (n_tiles & 1) * (2 * AT_BM);
+    xr[hf * AT_BM + r] = l_run;
+    named_bar_sync(1 + quarter, 64);
+    const float inv = 1.0f / (l_run + xr[(hf ^ 1) * AT_BM + r]);
+    const int q = q0 + r;
+    uint32_t v[32];
+    tmem_ld32(to, v);
+    tmem_ld_wait();
+    if (q < p.Lq) {
+      __nv_bfloat16* op = p.out + (static_cast<long long>(b) * p.Lq + q) * p.ld_o + head * AT_D + 32 * hf;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 w;
+        w.x = pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+        w.y = pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+        w.z = pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+        w.w = pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+        *reinterpret_cast<uint4*>(op + i) = w;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int launch_attn_ws(const tng_attn_desc* d, const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm,
+                          const AttnParams& p, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attention_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(TNG_ECUDA, "cudaFuncSetAttribute(attention_ws): %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  dim3 grid((d->Lq + AT_BM - 1) / AT_BM, d->heads, d->batch);
+  attention_ws_kernel<<<grid, AW_THREADS, AW_SMEM_BYTES, st>>>(qm, km, vm, p);
+  count_launch();
+  return check_launch("attention_ws");
+}
+
 template <int NSPLIT>
 static int launch_attn(const tng_attn_desc* d, const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm,
                        const AttnParams& p, cudaStream_t st) {
@@ -420,5 +732,9 @@ extern "C" int tng_attention(const tng_attn_desc* d, void* stream) {
     if (rc) return rc;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return d->nsplit == 1 ? launch_attn<1>(d, qm, km, vm, p, st) : launch_attn<2>(d, qm, km, vm, p, st);
+  if (d->nsplit == 2) return launch_attn<2>(d, qm, km, vm, p, st);
+  static int variant = -1;   // default: two-CTA-per-SM kernel (measured faster); TNG_ATTN=3 = warp-specialised kernel
+  if (variant < 0) { const char* e = getenv("TNG_ATTN"); variant = e ? atoi(e) : 2; }
+  if (variant == 3 && d->split_off == 0) return launch_attn_ws(d, qm, km, vm, p, st);
+  return launch_attn<1>(d, qm, km, vm, p, st);
 }

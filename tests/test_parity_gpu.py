@@ -173,3 +173,22 @@ def test_tiny_unet_long_clip_and_wide_text(cuda, precision):
     e = rel(out, ref)
     print(f"tiny UNet 768x16 / text dim 256 {precision}: rel err vs oracle {e:.3e}")
     assert e < TOL[precision]
+
+
+def test_tiny_inference_ddim_no_cfg_vs_oracle(cuda):
+    """DDIM sampler (BASELINE.json's metric names it) and the guidance_scale <= 1 branch (models.py:214,218-221)."""
+    cfg = synth.TINY_UNET_CONFIG
+    sd = synth.synth_state_dict(synth.unet_param_shapes(cfg), seed=0)
+    embeds, mask = synth.synth_conditioning(2, 9, cfg["cross_attention_dim"], seed=8, masked_tail=2)
+    embeds, mask = embeds[2:], mask[2:]            # conditional half only (no CFG)
+    lat0, _ = synth.synth_noise(2, 1, shape=(8, 32, 16), seed=21)
+    ref = opipe.inference(sd, cfg, osched.OracleDDIM(**osched.SD21_CONFIG), embeds, mask, 3, 1.0, lat0)
+    m = AudioDiffusion(unet_config=cfg, precision="split").to(cuda)
+    m.unet.load_state_dict(sd)
+    sch = DDIMScheduler.from_pretrained()
+    lat = m.inference(["a", "b"], sch, 3, 1.0, prompt_embeds=embeds, boolean_prompt_mask=mask, latents=lat0,
+                      latent_shape=(32, 16))
+    assert sch.timesteps.tolist() == [667, 334, 1]
+    e = rel(lat, ref)
+    print(f"tiny 3-step DDIM, no CFG (split): rel err vs oracle {e:.3e}")
+    assert e < 1e-3
