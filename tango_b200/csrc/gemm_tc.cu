@@ -67,8 +67,11 @@ struct GemmCfg {
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // per epilogue warp: 32 x 32 fp32 swizzled transpose tile
   static constexpr int STAGES_RAW = (227 * 1024 - EPI_BYTES - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int ACC_STRIDE = TMEM_COLS / 2;
+  static constexpr int TMEM_COLS = (4 * BN <= 128) ? 128 : (4 * BN <= 256) ? 256 : 512;  // one CTA per SM: take what helps
+  // accumulator stages in TMEM: as many as fit (2 for N tile 256, 3 for 160, 4 for <= 128): extra stages absorb the
+  // wake-up latency of the epilogue warps when the main loop of a tile is short (K = 320 linears)
+  static constexpr int NACC = (TMEM_COLS / BN) > 4 ? 4 : (TMEM_COLS / BN);
+  static constexpr int ACC_STRIDE = BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
 };
 
@@ -431,9 +434,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  constexpr int NACC = Cfg::NACC;
+  uint64_t* tfull_bar = bars + 2 * STAGES;          // [NACC]
+  uint64_t* tempty_bar = bars + 2 * STAGES + NACC;  // [NACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NACC);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -449,7 +453,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], CL == 2 ? 2 : 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NACC; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
     }
@@ -529,8 +533,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     uint32_t phase = 0;
     int it = 0;
     for (int tile = work0; tile < total_tiles; tile += work_stride, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = it % NACC;
+      const uint32_t aphase = (it / NACC) & 1;
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
@@ -575,8 +579,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       else if (p.bn == 1) nvalid = min(p.bh, p.H - h0) * p.bw;
       else nvalid = min(p.bn, p.NB - n0) * p.bh * p.bw;
       const int rpi = p.bw * p.bh;  // rows of one image inside a tile
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = it % NACC;
+      const uint32_t aphase = (it / NACC) & 1;
       const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (static_cast<uint32_t>(ew * 32) << 16);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();

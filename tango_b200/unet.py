@@ -86,6 +86,7 @@ class UNet2DConditionModel:
         self._packed = False
         self._bufs: Optional[_Buffers] = None
         self._cond = None
+        self.l2_chunk_mb = float(__import__("os").environ.get("TNG_L2_CHUNK_MB", "0"))  # 0 = off (experiment)
 
     # ----------------------------------------------------------------------------------------- diffusers-style API
     @staticmethod
@@ -293,6 +294,25 @@ class UNet2DConditionModel:
         return out
 
     def _transformer(self, name, t, x, NB, H, W, kv, bias, Lk, shared_half: bool = False):
+        """Transformer2DModel on rows. Large-activation levels are processed in batch chunks whose fp32 hidden state fits
+        comfortably in the 126 MB L2, so that the HBM-bound LayerNorm / K=C linears between the attention kernels find
+        their operands in L2 instead of HBM (the images of a batch are independent)."""
+        R, Cc = NB * H * W, t.C
+        chunk_bytes = self.l2_chunk_mb * 1e6
+        if (not shared_half) and chunk_bytes > 0 and R * Cc * 4 > chunk_bytes and NB % 2 == 0:
+            nchunks = 2
+            while (R // nchunks) * Cc * 4 > chunk_bytes and NB % (2 * nchunks) == 0:
+                nchunks *= 2
+            nb = NB // nchunks
+            out = self._buf(name, (R, Cc), torch.float32)
+            for ci in range(nchunks):
+                r0, r1 = ci * nb * H * W, (ci + 1) * nb * H * W
+                self._transformer_body(name + "_c", t, x[r0:r1], nb, H, W, kv[ci * nb * Lk:(ci + 1) * nb * Lk],
+                                       None if bias is None else bias[ci * nb:(ci + 1) * nb], Lk, out=out[r0:r1])
+            return out
+        return self._transformer_body(name, t, x, NB, H, W, kv, bias, Lk, shared_half=shared_half)
+
+    def _transformer_body(self, name, t, x, NB, H, W, kv, bias, Lk, shared_half: bool = False, out=None):
         """shared_half: `x` holds only the first NB/2 images and stands for both CFG halves (identical latents and
         timestep): everything up to the self-attention output is computed once and duplicated before the
         cross-attention, the first place where the two halves see different data."""
@@ -332,7 +352,8 @@ class UNet2DConditionModel:
         run_linear(t.ff1, n, out_bf16=ff)
         hsb = self._buf("hsb", (R, Cc * s), torch.bfloat16)
         run_linear(t.ff2, ff, res=hs, out_bf16=hsb)
-        out = self._buf(name, (R, Cc), torch.float32)
+        if out is None:
+            out = self._buf(name, (R, Cc), torch.float32)
         run_linear(t.proj_out, hsb, res=x, out_f32=out)
         return out
 
