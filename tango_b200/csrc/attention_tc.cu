@@ -365,6 +365,375 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
 
 
 // =====================================================================================================================
+// attention_sub_kernel — same data layout and occupancy as attention_tc_kernel (thread = query row, two CTAs per SM in
+// perf mode), but warp-specialised and software-pipelined at 64-key SUB-TILE granularity inside the CTA:
+//   * warps 0-3 (128 threads) only do softmax; warp 4 (one elected lane) owns TMA loads and every tcgen05.mma. The
+//     main loop has no CTA-wide barrier: softmax -> issuer through bar_p (128 arrivals: "P_g is in smem and S_g has
+//     been read"), issuer -> softmax through tcgen05.commit barriers;
+//   * S is double-buffered in TMEM (columns [0,64) and [64,128) = the two halves of a 128-key tile); Q K^T of sub-tile
+//     g+2 is issued as soon as sub-tile g has been handed over, so the softmax warps find S_{g+1} ready, and P V of
+//     sub-tile g runs underneath the softmax of g+1;
+//   * single pass over S: the exponent uses the running reference maximum (the lazy-rescale reference, at most 2^8
+//     below the true maximum), the sub-tile maximum is tracked on the fly and only when some row of the warp grew by
+//     more than 2^8 the warp rescales O / l and recomputes the sub-tile (first sub-tile: explicit maximum pass);
+//   * K and V tiles (128 keys) are loaded separately: a K buffer is free after Q K^T of both its halves, a V buffer
+//     after P V of both its halves, which keeps every TMA load about two sub-tiles ahead of its first use.
+// In-order tensor pipe => the commit that signals S_{g+2} also proves P V_g complete (P half and, for odd g, the V
+// buffer reusable); bar_pv is only waited on by the rare rescale path and at the end.
+constexpr int AS_SOFTMAX_THREADS = 128;
+constexpr int AS_THREADS = AS_SOFTMAX_THREADS + 32;
+
+__device__ __forceinline__ void softmax_bar_sync() {   // named barrier 1: the 128 softmax threads only
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(AS_THREADS, (NSPLIT == 1) ? 2 : 1)
+attention_sub_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                     const __grid_constant__ CUtensorMap vmap, const __grid_constant__ AttnParams p) {
+  using Cfg = AttnCfg<NSPLIT>;
+  constexpr int SUB = 64;                          // keys per sub-tile
+  constexpr int HALF_BYTES = SUB * 128;            // 64 K rows of a swizzled [128][64] chunk
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;                 // [NBUF][KV_BYTES]
+  uint8_t* sV = sK + AT_NBUF * Cfg::KV_BYTES;      // [NBUF][KV_BYTES]
+  uint8_t* sP = sV + AT_NBUF * Cfg::KV_BYTES;      // hi chunks 0,1 (= sub-tile halves) then lo chunks 0,1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* bar_q = bars;            // [1]
+  uint64_t* bar_k = bars + 1;        // [2] K tile landed
+  uint64_t* bar_v = bars + 3;        // [2] V tile landed
+  uint64_t* bar_s = bars + 5;        // [2] S half ready
+  uint64_t* bar_pv = bars + 7;       // [2] P V of a half drained
+  uint64_t* bar_p = bars + 9;        // [2] P half written + S half read (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  float* sbias = reinterpret_cast<float*>(sP + Cfg::P_BYTES + 128);  // per-sub-tile key bias (log2 domain), -inf = masked
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int q0 = blockIdx.x * AT_BM;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_tiles = (p.Lk + AT_BN - 1) / AT_BN;
+  const int n_sub = (p.Lk + SUB - 1) / SUB;
+
+  if (tid == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("[tng] attention: dynamic smem base not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&qmap);
+    tma_prefetch_desc(&kmap);
+    tma_prefetch_desc(&vmap);
+    for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bar_p[0], AS_SOFTMAX_THREADS);
+    mbar_init(&bar_p[1], AS_SOFTMAX_THREADS);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_s = tmem_base;
+  const uint32_t tm_o = tmem_base + 128;
+
+  if (warp == 4) {
+    // ================================================================= loader / MMA issuer (one elected lane)
+    if (lane == 0) {
+      auto load_k = [&](int tile) {
+        const int buf = tile % AT_NBUF;
+        mbar_arrive_expect_tx(&bar_k[buf], Cfg::KV_BYTES);
+#pragma unroll
+        for (int s = 0; s < NSPLIT; ++s)
+          tma_load_3d(sK + buf * Cfg::KV_BYTES + s * AT_CHUNK, &kmap, &bar_k[buf],
+                      p.k_col0 + s * p.k_lo_off + head * AT_D, tile * AT_BN, b);
+      };
+      auto load_v = [&](int tile) {
+        const int buf = tile % AT_NBUF;
+        mbar_arrive_expect_tx(&bar_v[buf], Cfg::KV_BYTES);
+#pragma unroll
+        for (int s = 0; s < NSPLIT; ++s)
+          tma_load_3d(sV + buf * Cfg::KV_BYTES + s * AT_CHUNK, &vmap, &bar_v[buf],
+                      p.v_col0 + s * p.v_lo_off + head * AT_D, tile * AT_BN, b);
+      };
+      // S[g & 1] = Q K_g^T over the 64 keys of sub-tile g (hi*hi [+ lo*hi + hi*lo])
+      auto issue_qk = [&](int g) {
+        const int buf = (g >> 1) % AT_NBUF, h = g & 1;
+        constexpr uint32_t idesc = umma_idesc_bf16(AT_BM, SUB, 0, 0);
+        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + buf * Cfg::KV_BYTES) + h * HALF_BYTES;
+        constexpr int NT = (NSPLIT == 1) ? 1 : 3;
+        const int qsel[3] = {0, 1, 0}, ksel[3] = {0, 0, 1};
+        uint32_t acc = 0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const uint64_t adesc = umma_desc_sw128(qa + qsel[t] * AT_CHUNK, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(ka + ksel[t] * AT_CHUNK, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < AT_D / 16; ++k) {
+            umma_bf16(tm_s + h * SUB, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&bar_s[h]);
+      };
+      // O (+)= P_g V_g   (A = P chunk g&1, K-major; B = V rows [64 h, 64 h + 16 nk16), MN-major: 16 keys = 2048 B)
+      auto issue_pv = [&](int g, uint32_t accumulate, int nk16) {
+        const int buf = (g >> 1) % AT_NBUF, h = g & 1;
+        constexpr uint32_t idesc = umma_idesc_bf16(AT_BM, AT_D, 0, 1);
+        const uint32_t pa = smem_u32(sP) + h * AT_CHUNK, va = smem_u32(sV + buf * Cfg::KV_BYTES) + h * HALF_BYTES;
+        constexpr int NT = (NSPLIT == 1) ? 1 : 3;
+        const int psel[3] = {0, 1, 0}, vsel[3] = {0, 0, 1};
+        uint32_t acc = accumulate;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+#pragma unroll
+          for (int k = 0; k < SUB / 16; ++k) {
+            if (k >= nk16) break;  // keys beyond the written P columns (short last sub-tile)
+            const uint64_t adesc = umma_desc_sw128(pa + psel[t] * 2 * AT_CHUNK, 16, 1024) + 2 * k;
+            const uint64_t bdesc = umma_desc_sw128(va + vsel[t] * AT_CHUNK + k * 2048, 1024, 1024);
+            umma_bf16(tm_o, adesc, bdesc, idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&bar_pv[h]);
+      };
+
+      mbar_arrive_expect_tx(bar_q, Cfg::Q_BYTES);
+#pragma unroll
+      for (int s = 0; s < NSPLIT; ++s)
+        tma_load_3d(sQ + s * AT_CHUNK, &qmap, bar_q, p.q_col0 + s * p.q_lo_off + head * AT_D, q0, b);
+      for (int t = 0; t < AT_NBUF && t < n_tiles; ++t) { load_k(t); load_v(t); }
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_k[0], 0);
+      tc_fence_after();
+      issue_qk(0);
+      if (n_sub > 1) issue_qk(1);
+      for (int g = 0; g < n_sub; ++g) {
+        const int h = g & 1, T = g >> 1;
+        const int kv0 = g * SUB;
+        const bool tail = (p.kbias != nullptr) || (kv0 + SUB > p.Lk);
+        const int ncols = tail ? min(SUB, ((p.Lk - kv0) + 31) & ~31) : SUB;   // same rule as the softmax warps
+        mbar_wait(&bar_p[h], T & 1);     // P_g written (and fenced to the async proxy), S_g fully read
+        mbar_wait(&bar_v[T % AT_NBUF], (T / AT_NBUF) & 1);
+        tc_fence_after();
+        issue_pv(g, g > 0 ? 1u : 0u, ncols / 16);
+        if (g + 2 < n_sub) {
+          const int T2 = (g + 2) >> 1;
+          mbar_wait(&bar_k[T2 % AT_NBUF], (T2 / AT_NBUF) & 1);
+          tc_fence_after();
+          issue_qk(g + 2);       // commits bar_s[h] after P V_g and Q K_{g+2}^T
+        }
+        if (h == 1) {
+          // softmax of g = 2T+1 is over => S_g was complete => both Q K^T of K tile T are done, and (commit order)
+          // P V of both halves of tile T-1 had drained before S_g was signalled
+          if (T + 2 < n_tiles) load_k(T + 2);
+          if (T >= 1 && T + 1 < n_tiles) load_v(T + 1);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================= softmax warps: thread = query row = TMEM lane
+    const int r = tid;
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t ts = tm_s + lane_addr;
+    const uint32_t to = tm_o + lane_addr;
+    float m_ref = -INFINITY;  // reference max used in the exponent (log2 domain)
+    float l_run = 0.f;
+    const float sc = p.scale_log2e;
+    const float* kb = p.kbias ? p.kbias + static_cast<long long>(b) * p.Lk : nullptr;
+    constexpr float LOG2E = 1.4426950408889634f;
+    uint8_t* prow_base = sP + r * 128;
+    const int rsw = r & 7;
+
+    for (int g = 0; g < n_sub; ++g) {
+      const int h = g & 1, T = g >> 1;
+      __syncwarp();
+      mbar_wait(&bar_s[h], T & 1);   // S_g complete; in-order tensor pipe => P V_{g-2} complete as well (P half free)
+      tc_fence_after();
+      const int kv0 = g * SUB;
+      const bool tail = (kb != nullptr) || (kv0 + SUB > p.Lk);
+      // columns actually processed in this sub-tile (multiple of 32); P columns beyond are never written nor multiplied
+      const int ncols = tail ? min(SUB, ((p.Lk - kv0) + 31) & ~31) : SUB;
+      if (tail) {
+        float bv = -INFINITY;
+        if (tid < SUB) {
+          const int kv = kv0 + tid;
+          if (kv < p.Lk) bv = kb ? kb[kv] * LOG2E : 0.f;
+        }
+        softmax_bar_sync();  // previous sub-tile's readers are done
+        if (tid < SUB) sbias[tid] = bv;
+        softmax_bar_sync();
+      }
+      const uint32_t tsh = ts + h * SUB;
+      if (g == 0) {
+        // explicit maximum pass for the very first sub-tile (no reference yet)
+        float m_tile = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < ncols; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tsh + c, v);
+          tmem_ld_wait();
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          if (!tail) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              m0 = fmaxf(m0, __uint_as_float(v[i]));
+              m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+              m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+            }
+            m_tile = fmaxf(m_tile, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sc);  // scale > 0
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              m0 = fmaxf(m0, fmaf(__uint_as_float(v[i]), sc, sbias[c + i]));
+              m1 = fmaxf(m1, fmaf(__uint_as_float(v[i + 1]), sc, sbias[c + i + 1]));
+              m2 = fmaxf(m2, fmaf(__uint_as_float(v[i + 2]), sc, sbias[c + i + 2]));
+              m3 = fmaxf(m3, fmaf(__uint_as_float(v[i + 3]), sc, sbias[c + i + 3]));
+            }
+            m_tile = fmaxf(m_tile, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+          }
+        }
+        m_ref = m_tile;
+      }
+      // ---- probabilities relative to m_ref -> bf16 (hi/lo) -> swizzled smem; at most two rounds (see header)
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int round = 0; round < 2; ++round) {
+        float xmax = -INFINITY;
+        lsum = 0.f;
+        uint8_t* prow = prow_base + h * AT_CHUNK;
+#pragma unroll 1
+        for (int c = 0; c < ncols; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tsh + c, v);
+          tmem_ld_wait();
+          float pr[32];
+          float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;                                  // independent partial sums (ILP)
+          float x0 = -INFINITY, x1 = -INFINITY, x2 = -INFINITY, x3 = -INFINITY;          // and partial maxima
+          if (!tail) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float a0 = fmaf(__uint_as_float(v[i]), sc, -m_ref), a1 = fmaf(__uint_as_float(v[i + 1]), sc, -m_ref);
+              const float a2 = fmaf(__uint_as_float(v[i + 2]), sc, -m_ref), a3 = fmaf(__uint_as_float(v[i + 3]), sc, -m_ref);
+              x0 = fmaxf(x0, a0); x1 = fmaxf(x1, a1); x2 = fmaxf(x2, a2); x3 = fmaxf(x3, a3);
+              pr[i] = ex2_approx(a0); pr[i + 1] = ex2_approx(a1); pr[i + 2] = ex2_approx(a2); pr[i + 3] = ex2_approx(a3);
+              l0 += pr[i]; l1 += pr[i + 1]; l2 += pr[i + 2]; l3 += pr[i + 3];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {   // ex2(-inf) = 0 for masked keys
+              const float a0 = fmaf(__uint_as_float(v[i]), sc, sbias[c + i]) - m_ref;
+              const float a1 = fmaf(__uint_as_float(v[i + 1]), sc, sbias[c + i + 1]) - m_ref;
+              const float a2 = fmaf(__uint_as_float(v[i + 2]), sc, sbias[c + i + 2]) - m_ref;
+              const float a3 = fmaf(__uint_as_float(v[i + 3]), sc, sbias[c + i + 3]) - m_ref;
+              x0 = fmaxf(x0, a0); x1 = fmaxf(x1, a1); x2 = fmaxf(x2, a2); x3 = fmaxf(x3, a3);
+              pr[i] = ex2_approx(a0); pr[i + 1] = ex2_approx(a1); pr[i + 2] = ex2_approx(a2); pr[i + 3] = ex2_approx(a3);
+              l0 += pr[i]; l1 += pr[i + 1]; l2 += pr[i + 2]; l3 += pr[i + 3];
+            }
+          }
+          lsum += (l0 + l1) + (l2 + l3);
+          xmax = fmaxf(xmax, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
+          const int u0 = c >> 3;  // first 16-byte unit inside the 128-byte row
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 w;
+            w.x = pack_bf16(pr[8 * u + 0], pr[8 * u + 1]);
+            w.y = pack_bf16(pr[8 * u + 2], pr[8 * u + 3]);
+            w.z = pack_bf16(pr[8 * u + 4], pr[8 * u + 5]);
+            w.w = pack_bf16(pr[8 * u + 6], pr[8 * u + 7]);
+            *reinterpret_cast<uint4*>(prow + (((u0 + u) ^ rsw) << 4)) = w;
+            if (NSPLIT == 2) {
+              float lo[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) lo[q] = pr[8 * u + q] - __bfloat162float(__float2bfloat16_rn(pr[8 * u + q]));
+              uint4 wl;
+              wl.x = pack_bf16(lo[0], lo[1]); wl.y = pack_bf16(lo[2], lo[3]);
+              wl.z = pack_bf16(lo[4], lo[5]); wl.w = pack_bf16(lo[6], lo[7]);
+              *reinterpret_cast<uint4*>(prow + 2 * AT_CHUNK + (((u0 + u) ^ rsw) << 4)) = wl;
+            }
+          }
+        }
+        // ---- lazy rescale (warp-uniform decision; tcgen05.ld/st are warp collectives)
+        const bool need = xmax > AT_LAZY;
+        if (round == 1 || !__any_sync(0xffffffffu, need)) break;
+        const float f = need ? ex2_approx(-xmax) : 1.0f;   // = 2^(m_ref - m_new), m_new = m_ref + xmax
+        l_run *= f;
+        if (g > 0) {
+          mbar_wait(&bar_pv[(g - 1) & 1], ((g - 1) >> 1) & 1);   // every P V issued so far has landed in O
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < AT_D; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(to + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st32(to + c, v);
+          }
+          tmem_st_wait();
+        }
+        if (need) m_ref += xmax;
+      }
+      l_run += lsum;
+      // hand-over: P (generic-proxy writes) visible to the tensor core (async proxy); S reads / O rescales are done
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bar_p[h]);
+    }
+
+    // ---- finalize: O / l -> bf16 (hi/lo)
+    __syncwarp();
+    mbar_wait(&bar_pv[(n_sub - 1) & 1], ((n_sub - 1) >> 1) & 1);
+    tc_fence_after();
+    const int q = q0 + r;
+    const float inv = 1.0f / l_run;
+    __nv_bfloat16* op = p.out + (static_cast<long long>(b) * p.Lq + q) * p.ld_o + head * AT_D;
+#pragma unroll
+    for (int c = 0; c < AT_D; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(to + c, v);
+      tmem_ld_wait();
+      if (q < p.Lq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float y[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(v[i + t]) * inv;
+          uint4 w;
+          w.x = pack_bf16(y[0], y[1]); w.y = pack_bf16(y[2], y[3]);
+          w.z = pack_bf16(y[4], y[5]); w.w = pack_bf16(y[6], y[7]);
+          *reinterpret_cast<uint4*>(op + c + i) = w;
+          if (p.split_off > 0) {
+            float lo[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) lo[t] = y[t] - __bfloat162float(__float2bfloat16_rn(y[t]));
+            uint4 wl;
+            wl.x = pack_bf16(lo[0], lo[1]); wl.y = pack_bf16(lo[2], lo[3]);
+            wl.z = pack_bf16(lo[4], lo[5]); wl.w = pack_bf16(lo[6], lo[7]);
+            *reinterpret_cast<uint4*>(op + p.split_off + c + i) = wl;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+
+// =====================================================================================================================
 // attention_ws_kernel — warp-specialised variant (perf mode, NSPLIT = 1): 8 softmax warps + 1 loader/issuer warp, one
 // CTA per SM. Two threads share a query row (warps w and w+4 own the two 64-key halves of the 128-key tile), S is
 // double-buffered in TMEM and the issuer keeps the tensor pipe one tile ahead:
@@ -675,6 +1044,23 @@ static int launch_attn_ws(const tng_attn_desc* d, const CUtensorMap& qm, const C
 }
 
 template <int NSPLIT>
+static int launch_attn_sub(const tng_attn_desc* d, const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm,
+                           const AttnParams& p, cudaStream_t st) {
+  using Cfg = AttnCfg<NSPLIT>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attention_sub_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(TNG_ECUDA, "cudaFuncSetAttribute(attention_sub): %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  dim3 grid((d->Lq + AT_BM - 1) / AT_BM, d->heads, d->batch);
+  attention_sub_kernel<NSPLIT><<<grid, AS_THREADS, Cfg::SMEM_BYTES, st>>>(qm, km, vm, p);
+  count_launch();
+  return check_launch("attention_sub");
+}
+
+template <int NSPLIT>
 static int launch_attn(const tng_attn_desc* d, const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm,
                        const AttnParams& p, cudaStream_t st) {
   using Cfg = AttnCfg<NSPLIT>;
@@ -732,9 +1118,12 @@ extern "C" int tng_attention(const tng_attn_desc* d, void* stream) {
     if (rc) return rc;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (d->nsplit == 2) return launch_attn<2>(d, qm, km, vm, p, st);
-  static int variant = -1;   // default: two-CTA-per-SM kernel (measured faster); TNG_ATTN=3 = warp-specialised kernel
-  if (variant < 0) { const char* e = getenv("TNG_ATTN"); variant = e ? atoi(e) : 2; }
+  // variants (TNG_ATTN): 4 = sub-tile pipelined kernel (default), 2 = tile-at-a-time kernel, 3 = warp-specialised
+  // one-CTA-per-SM kernel (perf mode only; measured slower)
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("TNG_ATTN"); variant = e ? atoi(e) : 4; }
+  if (d->nsplit == 2) return variant == 2 ? launch_attn<2>(d, qm, km, vm, p, st) : launch_attn_sub<2>(d, qm, km, vm, p, st);
   if (variant == 3 && d->split_off == 0) return launch_attn_ws(d, qm, km, vm, p, st);
-  return launch_attn<1>(d, qm, km, vm, p, st);
+  if (variant == 2) return launch_attn<1>(d, qm, km, vm, p, st);
+  return launch_attn_sub<1>(d, qm, km, vm, p, st);
 }

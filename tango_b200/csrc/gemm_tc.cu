@@ -357,7 +357,7 @@ __device__ __noinline__ void epi_tile_generic(const GemmKernelParams& p, float* 
 // GEGLU: columns [0, BN/2) of the tile are "hidden", [BN/2, BN) the matching "gate" (weights interleaved on the
 // host). out[:, tn*BN/2 + j] = (hid + b) * gelu_erf(gate + b'). Rows r0 + 4i (consecutive-row tiles); rows >= nvalid
 // are skipped.
-template <int BN>
+template <int BN, bool FULL, bool SPLIT>
 __device__ __forceinline__ void epi_tile_geglu(const GemmKernelParams& p, float* st, long long r0, int nleft,
                                                uint32_t taddr, int tn, int lane, int hf) {
   constexpr int HALF = BN / 2;
@@ -365,7 +365,7 @@ __device__ __forceinline__ void epi_tile_geglu(const GemmKernelParams& p, float*
 #pragma unroll 1
   for (int c = hf * 32; c < HALF; c += 64) {
     uint32_t v[32];
-    float4 hid[8];
+    float4 hid[8], g[8];
     tmem_ld32(taddr + c, v);
     tmem_ld_wait();
     __syncwarp();
@@ -381,6 +381,11 @@ __device__ __forceinline__ void epi_tile_geglu(const GemmKernelParams& p, float*
     __syncwarp();
     epi_stage(st, lane, v);
     __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + rsub;
+      g[i] = *reinterpret_cast<const float4*>(st + r * 32 + ((cg ^ (r & 7)) << 2));
+    }
     const int gcol = tn * BN + c + 4 * cg;  // GEMM column of the hidden half; gate at + HALF
     const int ocol = tn * HALF + c + 4 * cg;
     float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
@@ -388,24 +393,28 @@ __device__ __forceinline__ void epi_tile_geglu(const GemmKernelParams& p, float*
       bh = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
       bg = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + HALF));
     }
+    // branch-free arithmetic over all 32 values of this lane (32 independent MUFU chains to interleave)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      hid[i].x = (hid[i].x + bh.x) * gelu_erf_f(g[i].x + bg.x);
+      hid[i].y = (hid[i].y + bh.y) * gelu_erf_f(g[i].y + bg.y);
+      hid[i].z = (hid[i].z + bh.z) * gelu_erf_f(g[i].z + bg.z);
+      hid[i].w = (hid[i].w + bh.w) * gelu_erf_f(g[i].w + bg.w);
+    }
     __nv_bfloat16* op = p.out_bf16 + r0 * p.ld_bf16 + ocol;
     const long long os = 4 * p.ld_bf16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int r = 4 * i + rsub;
-      const float4 g = *reinterpret_cast<const float4*>(st + r * 32 + ((cg ^ (r & 7)) << 2));
-      if (4 * i >= nleft) continue;
-      const float y0 = (hid[i].x + bh.x) * gelu_erf_f(g.x + bg.x);
-      const float y1 = (hid[i].y + bh.y) * gelu_erf_f(g.y + bg.y);
-      const float y2 = (hid[i].z + bh.z) * gelu_erf_f(g.z + bg.z);
-      const float y3 = (hid[i].w + bh.w) * gelu_erf_f(g.w + bg.w);
+      if (!FULL && 4 * i >= nleft) continue;
       uint2 u;
-      u.x = pack_bf16(y0, y1); u.y = pack_bf16(y2, y3);
+      u.x = pack_bf16(hid[i].x, hid[i].y); u.y = pack_bf16(hid[i].z, hid[i].w);
       *reinterpret_cast<uint2*>(op + i * os) = u;
-      if (p.split_off > 0) {
+      if (SPLIT) {
         uint2 l;
-        l.x = pack_bf16(y0 - __bfloat162float(__float2bfloat16_rn(y0)), y1 - __bfloat162float(__float2bfloat16_rn(y1)));
-        l.y = pack_bf16(y2 - __bfloat162float(__float2bfloat16_rn(y2)), y3 - __bfloat162float(__float2bfloat16_rn(y3)));
+        l.x = pack_bf16(hid[i].x - __bfloat162float(__float2bfloat16_rn(hid[i].x)),
+                        hid[i].y - __bfloat162float(__float2bfloat16_rn(hid[i].y)));
+        l.y = pack_bf16(hid[i].z - __bfloat162float(__float2bfloat16_rn(hid[i].z)),
+                        hid[i].w - __bfloat162float(__float2bfloat16_rn(hid[i].w)));
         *reinterpret_cast<uint2*>(op + p.split_off + i * os) = l;
       }
     }
@@ -599,7 +608,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
         }
       } else if (geglu) {
         // slot i of this lane is row ew*32 + rsub + 4i; rows below nvalid are valid
-        epi_tile_geglu<BN>(p, st, row_base + ew * 32 + rsub, nvalid - (ew * 32 + rsub), taddr, tn, lane, hf);
+        if constexpr (BN == 128 || BN == 256) {   // the host only selects these N tiles for GEGLU
+          const long long gr0 = row_base + ew * 32 + rsub;
+          const int nleft = nvalid - (ew * 32 + rsub);
+          if (p.split_off > 0) epi_tile_geglu<BN, false, true>(p, st, gr0, nleft, taddr, tn, lane, hf);
+          else if (nvalid == BM) epi_tile_geglu<BN, true, false>(p, st, gr0, nleft, taddr, tn, lane, hf);
+          else epi_tile_geglu<BN, false, false>(p, st, gr0, nleft, taddr, tn, lane, hf);
+        }
       } else if (!full) {
         EpiRows R;
         R.valid = 0;
