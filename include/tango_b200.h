@@ -27,6 +27,7 @@ extern "C" {
 #define TNG_ACT_SILU 1
 #define TNG_ACT_LRELU 2 /* slope = act_param */
 #define TNG_ACT_GEGLU 3 /* out[j] = acc[j] * gelu_erf(acc[j + BN/2]) within each N tile (weights pre-interleaved) */
+#define TNG_ACT_GEGLU_TANH 4 /* same pairing with the tanh-form GELU ("gelu_new": T5 v1.1 gated feed-forward) */
 
 #define TNG_DT_F32 0
 #define TNG_DT_BF16 1
@@ -143,6 +144,28 @@ int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, const void* x1,
 /* LayerNorm over the last dim of fp32 [rows, C] -> bf16 (attention.py:259,267,274). */
 int tng_layernorm(const float* x, int64_t rows, int64_t C, const float* gamma, const float* beta, float eps,
                   void* y, int64_t ld_y, int32_t split_off, void* stream);
+
+/* ---- text-conditioning front-end: FLAN-T5 encoder as called from models.py:98-100 (T5EncoderModel),
+ * models.py:129-147 (encode_text) and models.py:266-305 (encode_text_classifier_free). The arithmetic lives in the pip
+ * dependency `transformers` (models/t5/modeling_t5.py: T5LayerNorm, T5Attention, T5DenseGatedActDense, T5Stack), which is
+ * not under /root/reference; the entry points below replace those modules, the projections run through tng_conv_gemm. */
+
+/* T5LayerNorm: y = x * rsqrt(mean(x^2) + eps) * gamma over the last dim of fp32 [rows, C] -> bf16 y (+ lo half) and/or a
+ * dense fp32 copy y_f32 [rows, C] (the final_layer_norm output handed to the UNet); either output may be NULL. */
+int tng_rmsnorm(const float* x, int64_t rows, int64_t C, const float* gamma, float eps, void* y, int64_t ld_y,
+                int32_t split_off, float* y_f32, void* stream);
+/* nn.Embedding lookup (T5Stack.embed_tokens): out[r, :] = table[ids[r], :], fp32 [rows, C]; ids are int64 and must lie in
+ * [0, n_table_rows) (checked by the caller, as nn.Embedding's own index check is host-side on CPU). */
+int tng_gather_rows(const float* table, int64_t n_table_rows, const int64_t* ids, int64_t rows, int64_t C, float* out,
+                    void* stream);
+/* T5Attention.forward core for head width 64: softmax(q k^T + relbias[h, key - query] + kbias[b, key]) v, no score
+ * scaling. qkv: fp32 [batch*L, ld] with the q / k / v blocks of `heads*64` columns at q_col0 / k_col0 / v_col0;
+ * relbias: fp32 [heads, 2L-1] (index key - query + L - 1; the bucketed relative_attention_bias of block 0, shared by all
+ * blocks); kbias: fp32 [batch, L] additive key mask (0 or finfo.min, as get_extended_attention_mask builds it) or NULL;
+ * out: bf16 [batch*L, ld_o] (+ lo half at split_off). */
+int tng_rel_attention(const float* qkv, int64_t ld, int32_t q_col0, int32_t k_col0, int32_t v_col0, int32_t batch,
+                      int32_t heads, int32_t L, const float* relbias, const float* kbias, void* out, int64_t ld_o,
+                      int32_t split_off, void* stream);
 
 /* fp32 [rows, C] -> bf16 [rows, ld_y] with optional activation, optional hi/lo split, optional nearest x2
  * upsample of an (NB, H, W) grid (resnet.py:146; modules.py:53-57) — the cast in front of a conv that consumes

@@ -202,10 +202,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, 
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // one warp per row; the row is cached in registers (NI float4 per lane, C <= 128 * NI) so the variance is the exact
 // two-pass form; NI is a template parameter so that no predicated-off iterations are issued.
-template <int NI>
+template <int NI, bool RMS>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long long rows, int C, const float* gamma,
                                                          const float* beta, float eps, __nv_bfloat16* y, long long ld_y,
-                                                         int split_off) {
+                                                         int split_off, float* yf) {
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long lon
     v[i] = (q < Q) ? *reinterpret_cast<const float4*>(xr + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
-  const float mean = warp_sum(s) / C;
+  const float mean = RMS ? 0.f : warp_sum(s) / C;   // RMS (T5LayerNorm): no centring, no bias
   float sq = 0.f;
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
@@ -236,13 +236,113 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long lon
     const int q = lane + i * 32;
     if (q < Q) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + q * 4));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + q * 4));
+      const float4 b = RMS ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(beta + q * 4));
       float4 o;
       o.x = (v[i].x - mean) * rstd * g.x + b.x;
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z;
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      store4_split(yr + q * 4, o, split_off);
+      if (y) store4_split(yr + q * 4, o, split_off);
+      if (yf) *reinterpret_cast<float4*>(yf + row * C + q * 4) = o;   // optional fp32 copy (dense rows)
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ T5 front-end
+// Embedding lookup: out[r, :] = table[ids[r], :] (fp32), one warp per row.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* table, const long long* ids, long long rows, int C,
+                                                           float* out) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* src = reinterpret_cast<const float4*>(table + ids[row] * C);
+  float4* dst = reinterpret_cast<float4*>(out + row * C);
+  for (int q = lane; q < C / 4; q += 32) dst[q] = __ldg(src + q);
+}
+
+// Self-attention with an additive (head, key - query) position bias and an additive per-key mask bias, no score
+// scaling, head width 64 (T5Attention.forward of the `transformers` dependency): fp32 in, fp32 arithmetic, bf16 out.
+// The sequences are short (<= 512 tokens), so this is a plain SIMT kernel: one CTA per (batch, head, 16 queries),
+// each warp owns 4 queries; K / V stream through smem in 64-key tiles with an online softmax; lane j scores keys
+// j and j + 32, lane d accumulates output dims d and d + 32.
+constexpr int RA_KT = 64, RA_QPB = 16;
+__global__ void __launch_bounds__(128) rel_attention_kernel(const float* qkv, long long ld, int q_col0, int k_col0,
+                                                             int v_col0, int heads, int L, const float* relbias,
+                                                             const float* kbias, __nv_bfloat16* out, long long ld_o,
+                                                             int split_off) {
+  __shared__ float sK[RA_KT][65];
+  __shared__ float sV[RA_KT][65];
+  __shared__ float sQ[4][64];
+  __shared__ float sP[4][RA_KT];
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* base = qkv + static_cast<long long>(b) * L * ld + h * 64;
+  const float* rb = relbias + static_cast<long long>(h) * (2 * L - 1) + (L - 1);   // rb[key - query]
+  const float* kb = kbias ? kbias + static_cast<long long>(b) * L : nullptr;
+  const int q_first = blockIdx.y * RA_QPB + warp * 4;
+  float m[4], l[4], o0[4], o1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; l[i] = 0.f; o0[i] = 0.f; o1[i] = 0.f; }
+  for (int k0 = 0; k0 < L; k0 += RA_KT) {
+    __syncthreads();   // previous tile fully consumed
+    for (int e = threadIdx.x; e < RA_KT * 64; e += blockDim.x) {
+      const int j = e >> 6, d = e & 63;
+      const bool ok = (k0 + j) < L;
+      sK[j][d] = ok ? base[static_cast<long long>(k0 + j) * ld + k_col0 + d] : 0.f;
+      sV[j][d] = ok ? base[static_cast<long long>(k0 + j) * ld + v_col0 + d] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      const int q = q_first + i;
+      if (q >= L) break;   // warp-uniform
+      __syncwarp();
+      sQ[warp][lane] = base[static_cast<long long>(q) * ld + q_col0 + lane];
+      sQ[warp][lane + 32] = base[static_cast<long long>(q) * ld + q_col0 + lane + 32];
+      __syncwarp();
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll 16
+      for (int d = 0; d < 64; ++d) {
+        const float qd = sQ[warp][d];
+        s0 = fmaf(qd, sK[lane][d], s0);
+        s1 = fmaf(qd, sK[lane + 32][d], s1);
+      }
+      const int j0 = k0 + lane, j1 = k0 + lane + 32;
+      // scores += position_bias (relative bias + extended mask), as in T5Attention.forward
+      s0 = (j0 < L) ? s0 + (rb[j0 - q] + (kb ? kb[j0] : 0.f)) : -INFINITY;
+      s1 = (j1 < L) ? s1 + (rb[j1 - q] + (kb ? kb[j1] : 0.f)) : -INFINITY;
+      const float m_new = fmaxf(m[i], warp_max(fmaxf(s0, s1)));
+      const float corr = (m[i] == -INFINITY) ? 0.f : expf(m[i] - m_new);
+      const float p0 = (j0 < L) ? expf(s0 - m_new) : 0.f;
+      const float p1 = (j1 < L) ? expf(s1 - m_new) : 0.f;
+      l[i] = l[i] * corr + warp_sum(p0 + p1);
+      m[i] = m_new;
+      sP[warp][lane] = p0;
+      sP[warp][lane + 32] = p1;
+      __syncwarp();
+      float a0 = o0[i] * corr, a1 = o1[i] * corr;
+#pragma unroll 16
+      for (int j = 0; j < RA_KT; ++j) {
+        const float pj = sP[warp][j];
+        a0 = fmaf(pj, sV[j][lane], a0);
+        a1 = fmaf(pj, sV[j][lane + 32], a1);
+      }
+      o0[i] = a0; o1[i] = a1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = q_first + i;
+    if (q >= L) break;
+    const float inv = 1.0f / l[i];
+    __nv_bfloat16* op = out + (static_cast<long long>(b) * L + q) * ld_o + h * 64;
+    const float y0 = o0[i] * inv, y1 = o1[i] * inv;
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+    op[lane] = h0;
+    op[lane + 32] = h1;
+    if (split_off > 0) {
+      op[split_off + lane] = __float2bfloat16_rn(y0 - __bfloat162float(h0));
+      op[split_off + lane + 32] = __float2bfloat16_rn(y1 - __bfloat162float(h1));
     }
   }
 }
@@ -518,11 +618,11 @@ extern "C" int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, cons
 
 extern "C" int tng_layernorm(const float* x, int64_t rows, int64_t C, const float* gamma, const float* beta, float eps,
                              void* y, int64_t ld_y, int32_t split_off, void* stream) {
-  if (!x || !y || C % 4 || C > 2048 || ld_y % 4 || split_off % 4) return set_error(TNG_EINVAL, "layernorm: C=%lld unsupported", (long long)C);
+  if (!x || !y || !gamma || !beta || C % 4 || C > 2048 || ld_y % 4 || split_off % 4) return set_error(TNG_EINVAL, "layernorm: C=%lld unsupported", (long long)C);
   const int wpb = 8;
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
   const int ni = (int)((C / 4 + 31) / 32);
-#define TNG_LN(NI) layernorm_kernel<NI><<<grid, wpb * 32, 0, ST(stream)>>>(x, rows, (int)C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off)
+#define TNG_LN(NI) layernorm_kernel<NI, false><<<grid, wpb * 32, 0, ST(stream)>>>(x, rows, (int)C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off, nullptr)
   if (ni <= 1) TNG_LN(1);
   else if (ni <= 2) TNG_LN(2);
   else if (ni <= 3) TNG_LN(3);
@@ -532,6 +632,48 @@ extern "C" int tng_layernorm(const float* x, int64_t rows, int64_t C, const floa
 #undef TNG_LN
   count_launch();
   return check_launch("layernorm");
+}
+
+extern "C" int tng_rmsnorm(const float* x, int64_t rows, int64_t C, const float* gamma, float eps, void* y, int64_t ld_y,
+                           int32_t split_off, float* y_f32, void* stream) {
+  if (!x || (!y && !y_f32) || !gamma || C % 4 || C > 2048 || ld_y % 4 || split_off % 4) return set_error(TNG_EINVAL, "rmsnorm: C=%lld unsupported", (long long)C);
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  const int ni = (int)((C / 4 + 31) / 32);
+  const float* beta = nullptr;
+#define TNG_RMS(NI) layernorm_kernel<NI, true><<<grid, wpb * 32, 0, ST(stream)>>>(x, rows, (int)C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off, y_f32)
+  if (ni <= 1) TNG_RMS(1);
+  else if (ni <= 2) TNG_RMS(2);
+  else if (ni <= 3) TNG_RMS(3);
+  else if (ni <= 5) TNG_RMS(5);
+  else if (ni <= 10) TNG_RMS(10);
+  else TNG_RMS(16);
+#undef TNG_RMS
+  count_launch();
+  return check_launch("rmsnorm");
+}
+
+extern "C" int tng_gather_rows(const float* table, int64_t n_table_rows, const int64_t* ids, int64_t rows, int64_t C,
+                               float* out, void* stream) {
+  if (!table || !ids || !out || rows <= 0 || n_table_rows <= 0 || C % 4 ||
+      ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15))
+    return set_error(TNG_EINVAL, "gather_rows: bad argument");
+  const int wpb = 8;
+  gather_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, ST(stream)>>>(
+      table, reinterpret_cast<const long long*>(ids), rows, (int)C, out);
+  count_launch();
+  return check_launch("gather_rows");
+}
+
+extern "C" int tng_rel_attention(const float* qkv, int64_t ld, int32_t q_col0, int32_t k_col0, int32_t v_col0,
+                                 int32_t batch, int32_t heads, int32_t L, const float* relbias, const float* kbias,
+                                 void* out, int64_t ld_o, int32_t split_off, void* stream) {
+  if (!qkv || !relbias || !out || batch <= 0 || heads <= 0 || L <= 0) return set_error(TNG_EINVAL, "rel_attention: bad argument");
+  dim3 grid((unsigned)(batch * heads), (unsigned)((L + RA_QPB - 1) / RA_QPB));
+  rel_attention_kernel<<<grid, 128, 0, ST(stream)>>>(qkv, ld, q_col0, k_col0, v_col0, heads, L, relbias, kbias,
+                                                      reinterpret_cast<__nv_bfloat16*>(out), ld_o, split_off);
+  count_launch();
+  return check_launch("rel_attention");
 }
 
 extern "C" int tng_cast_act(const float* x, int64_t NB, int64_t H, int64_t W, int64_t C, int64_t ld_x,

@@ -357,7 +357,7 @@ __device__ __noinline__ void epi_tile_generic(const GemmKernelParams& p, float* 
 // GEGLU: columns [0, BN/2) of the tile are "hidden", [BN/2, BN) the matching "gate" (weights interleaved on the
 // host). out[:, tn*BN/2 + j] = (hid + b) * gelu_erf(gate + b'). Rows r0 + 4i (consecutive-row tiles); rows >= nvalid
 // are skipped.
-template <int BN, bool FULL, bool SPLIT>
+template <int BN, bool FULL, bool SPLIT, bool TANH>
 __device__ __forceinline__ void epi_tile_geglu(const GemmKernelParams& p, float* st, long long r0, int nleft,
                                                uint32_t taddr, int tn, int lane, int hf) {
   constexpr int HALF = BN / 2;
@@ -396,10 +396,10 @@ __device__ __forceinline__ void epi_tile_geglu(const GemmKernelParams& p, float*
     // branch-free arithmetic over all 32 values of this lane (32 independent MUFU chains to interleave)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      hid[i].x = (hid[i].x + bh.x) * gelu_erf_f(g[i].x + bg.x);
-      hid[i].y = (hid[i].y + bh.y) * gelu_erf_f(g[i].y + bg.y);
-      hid[i].z = (hid[i].z + bh.z) * gelu_erf_f(g[i].z + bg.z);
-      hid[i].w = (hid[i].w + bh.w) * gelu_erf_f(g[i].w + bg.w);
+      hid[i].x = (hid[i].x + bh.x) * (TANH ? gelu_tanh_f(g[i].x + bg.x) : gelu_erf_f(g[i].x + bg.x));
+      hid[i].y = (hid[i].y + bh.y) * (TANH ? gelu_tanh_f(g[i].y + bg.y) : gelu_erf_f(g[i].y + bg.y));
+      hid[i].z = (hid[i].z + bh.z) * (TANH ? gelu_tanh_f(g[i].z + bg.z) : gelu_erf_f(g[i].z + bg.z));
+      hid[i].w = (hid[i].w + bh.w) * (TANH ? gelu_tanh_f(g[i].w + bg.w) : gelu_erf_f(g[i].w + bg.w));
     }
     __nv_bfloat16* op = p.out_bf16 + r0 * p.ld_bf16 + ocol;
     const long long os = 4 * p.ld_bf16;
@@ -573,7 +573,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     float* st = sEpi + (warp - 4) * (32 * 32);
     const int rsub = lane >> 3;
     const int mode = (p.res ? 1 : 0) | (p.out_f32 ? 2 : 0) | (p.out_bf16 ? 4 : 0);
-    const bool geglu = (p.act == TNG_ACT_GEGLU);
+    const bool geglu = (p.act == TNG_ACT_GEGLU || p.act == TNG_ACT_GEGLU_TANH);
     int it = 0;
     for (int tile = work0; tile < total_tiles; tile += work_stride, ++it) {
       const int tm = (tile / p.n_tiles) * CLUSTER + crank, tn = tile % p.n_tiles;
@@ -611,9 +611,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
         if constexpr (BN == 128 || BN == 256) {   // the host only selects these N tiles for GEGLU
           const long long gr0 = row_base + ew * 32 + rsub;
           const int nleft = nvalid - (ew * 32 + rsub);
-          if (p.split_off > 0) epi_tile_geglu<BN, false, true>(p, st, gr0, nleft, taddr, tn, lane, hf);
-          else if (nvalid == BM) epi_tile_geglu<BN, true, false>(p, st, gr0, nleft, taddr, tn, lane, hf);
-          else epi_tile_geglu<BN, false, false>(p, st, gr0, nleft, taddr, tn, lane, hf);
+          if (p.act == TNG_ACT_GEGLU_TANH) {   // T5 front-end (small): one general instantiation
+            if (p.split_off > 0) epi_tile_geglu<BN, false, true, true>(p, st, gr0, nleft, taddr, tn, lane, hf);
+            else epi_tile_geglu<BN, false, false, true>(p, st, gr0, nleft, taddr, tn, lane, hf);
+          } else if (p.split_off > 0) epi_tile_geglu<BN, false, true, false>(p, st, gr0, nleft, taddr, tn, lane, hf);
+          else if (nvalid == BM) epi_tile_geglu<BN, true, false, false>(p, st, gr0, nleft, taddr, tn, lane, hf);
+          else epi_tile_geglu<BN, false, false, false>(p, st, gr0, nleft, taddr, tn, lane, hf);
         }
       } else if (!full) {
         EpiRows R;
@@ -739,7 +742,7 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   p.Ncols = (int)d->Ncols;
 
   int bn_tile = d->block_n;
-  if (d->act == TNG_ACT_GEGLU) {
+  if (d->act == TNG_ACT_GEGLU || d->act == TNG_ACT_GEGLU_TANH) {
     if (bn_tile == 0) bn_tile = (d->Ncols % 256 == 0) ? 256 : 128;
     if ((bn_tile != 128 && bn_tile != 256) || d->Ncols % bn_tile != 0 || !d->out_bf16 || d->out_f32 || d->res ||
         d->rowvec)
@@ -801,7 +804,7 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
     if (dbg < 0) { const char* e = getenv("TNG_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
     p.dbg = dbg;
   }
-  if (d->act == TNG_ACT_GEGLU && !vec) return set_error(TNG_EINVAL, "GEGLU epilogue needs 16-byte aligned output");
+  if ((d->act == TNG_ACT_GEGLU || d->act == TNG_ACT_GEGLU_TANH) && !vec) return set_error(TNG_EINVAL, "GEGLU epilogue needs 16-byte aligned output");
 
   // cluster of 2 CTAs along M sharing (multicasting) the weight tile: whenever there are at least two M tiles
   // launch mode: 1 = single CTA, 2 = cluster-of-2 weight multicast, 3 = CTA pair (tcgen05 cta_group::2).

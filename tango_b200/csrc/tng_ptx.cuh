@@ -357,6 +357,12 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   const float phi = x >= 0.0f ? 1.0f - q : q;
   return x * phi;
 }
+// GELU, tanh form ("gelu_new" of the T5 v1.1 / FLAN-T5 gated feed-forward):
+// 0.5 x (1 + tanh(u)) = x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3); 2 MUFU, relative error ~3e-7.
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float w = x * fmaf(x * x, 0.044715f, 1.0f);
+  return x * rcp_approx(1.0f + ex2_approx(w * -2.3022081986f));   // 2 sqrt(2/pi) log2(e)
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -14,7 +14,7 @@ import torch
 
 from . import build as _build
 
-ACT_NONE, ACT_SILU, ACT_LRELU, ACT_GEGLU = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_LRELU, ACT_GEGLU, ACT_GEGLU_TANH = 0, 1, 2, 3, 4
 DT_F32, DT_BF16 = 0, 1
 MAX_AVIEWS, MAX_KGROUPS = 4, 40
 
@@ -23,7 +23,7 @@ SYMBOLS = [
     "tng_version", "tng_last_error", "tng_launch_count", "tng_conv_gemm", "tng_attention",
     "tng_groupnorm_stats", "tng_groupnorm_apply", "tng_layernorm", "tng_cast_act", "tng_softmax_rows",
     "tng_transpose_bf16", "tng_sched_step", "tng_timestep_embedding", "tng_linear_f32", "tng_convt_gather",
-    "tng_tanh_to_i16",
+    "tng_tanh_to_i16", "tng_rmsnorm", "tng_gather_rows", "tng_rel_attention",
 ]
 
 
@@ -94,6 +94,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "tng_groupnorm_apply": [vp, i32, i64, vp, i32, i64, i64, i64, i32, vp, vp, vp, f32, i32, vp, i64, i32, vp,
                                 i64, i32, vp],
         "tng_layernorm": [vp, i64, i64, vp, vp, f32, vp, i64, i32, vp],
+        "tng_rmsnorm": [vp, i64, i64, vp, f32, vp, i64, i32, vp, vp],
+        "tng_gather_rows": [vp, i64, vp, i64, i64, vp, vp],
+        "tng_rel_attention": [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, i32, vp],
         "tng_cast_act": [vp, i64, i64, i64, i64, i64, i32, i32, f32, vp, i64, i32, vp],
         "tng_softmax_rows": [vp, i64, i64, i64, f32, vp, i64, i32, vp],
         "tng_transpose_bf16": [vp, i64, i64, i64, i64, vp, i64, vp],
@@ -294,6 +297,29 @@ def layernorm(x, gamma, beta, eps, y, *, split_off=0):
     rows, Cc = x.shape
     check(load().tng_layernorm(x.data_ptr(), rows, Cc, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(),
                                y.stride(0), split_off, stream_ptr()), "tng_layernorm")
+
+
+def rmsnorm(x, gamma, eps, y=None, *, split_off=0, y_f32=None):
+    require_cuda(x, gamma)
+    rows, Cc = x.shape
+    check(load().tng_rmsnorm(x.data_ptr(), rows, Cc, gamma.data_ptr(), eps, y.data_ptr() if y is not None else None,
+                             y.stride(0) if y is not None else 0, split_off,
+                             y_f32.data_ptr() if y_f32 is not None else None, stream_ptr()), "tng_rmsnorm")
+
+
+def gather_rows(table, ids, out):
+    require_cuda(table, ids, out)
+    if ids.dtype != torch.int64 or not ids.is_contiguous():
+        raise TangoB200Error("gather_rows: ids must be a contiguous int64 tensor")
+    check(load().tng_gather_rows(table.data_ptr(), table.shape[0], ids.data_ptr(), ids.numel(), table.shape[1],
+                                 out.data_ptr(), stream_ptr()), "tng_gather_rows")
+
+
+def rel_attention(qkv, relbias, kbias, out, *, batch, heads, L, q_col0, k_col0, v_col0, split_off=0):
+    require_cuda(qkv, relbias, out)
+    check(load().tng_rel_attention(qkv.data_ptr(), qkv.stride(0), q_col0, k_col0, v_col0, batch, heads, L,
+                                   relbias.data_ptr(), kbias.data_ptr() if kbias is not None else None,
+                                   out.data_ptr(), out.stride(0), split_off, stream_ptr()), "tng_rel_attention")
 
 
 def cast_act(x, NB, H, W, y, *, Cc=None, upsample2x=False, act=ACT_NONE, act_param=0.0, split_off=0):

@@ -38,7 +38,7 @@ class PackedConv:
 
     def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], *, split: bool, device, dilation: int = 1,
                  stride: int = 1, sc_w: Optional[torch.Tensor] = None, sc_b: Optional[torch.Tensor] = None,
-                 geglu_bn: int = 0, pad: Optional[int] = None):
+                 geglu_bn: int = 0, pad: Optional[int] = None, geglu_tanh: bool = False):
         w = w.detach().float()
         if w.dim() == 2:
             w = w[:, :, None, None]
@@ -57,6 +57,7 @@ class PackedConv:
         self.stride = stride
         self.split = split
         self.geglu_bn = geglu_bn
+        self.geglu_act = L.ACT_GEGLU_TANH if geglu_tanh else L.ACT_GEGLU
         wk = w.permute(0, 2, 3, 1).reshape(self.cout, len(taps) * self.cin)  # [Cout, tap*Cin]
         self.k_main = wk.shape[1]
         self.cin_sc = 0
@@ -182,7 +183,7 @@ def run_conv(pc: PackedConv, x: torch.Tensor, NB: int, H: int, W: int, *, sc_x: 
     if out_bf16 is not None and split:
         so = out_bf16.shape[-1] // 2
     if pc.geglu_bn:
-        act, block_n = L.ACT_GEGLU, pc.geglu_bn
+        act, block_n = pc.geglu_act, pc.geglu_bn
     L.conv_gemm(views, groups, pc.weight, Wo, Ho, NB, bias=pc.bias, rowvec=rowvec, res=res, alpha=alpha,
                 accumulate=accumulate, out_f32=out_f32, out_bf16=out_bf16, act=act, act_param=act_param,
                 split_off=so, block_n=block_n, rowvec_ld=rowvec_ld,

@@ -197,11 +197,45 @@ def vae_decoder_param_shapes(vae_cfg: dict = VAE_CONFIG) -> Shapes:
     return s
 
 
+TINY_T5_CONFIG = {"vocab_size": 96, "d_model": 128, "d_kv": 64, "num_heads": 2, "d_ff": 256, "num_layers": 2,
+                  "relative_attention_num_buckets": 32, "relative_attention_max_distance": 128,
+                  "layer_norm_epsilon": 1e-6, "feed_forward_proj": "gated-gelu"}
+# google/flan-t5-large (Tango, Tango 2) and google/flan-t5-xl (the XL UNet config) encoder stacks
+FLAN_T5_LARGE_CONFIG = dict(TINY_T5_CONFIG, vocab_size=32128, d_model=1024, num_heads=16, d_ff=2816, num_layers=24)
+FLAN_T5_XL_CONFIG = dict(TINY_T5_CONFIG, vocab_size=32128, d_model=2048, num_heads=32, d_ff=5120, num_layers=24)
+
+
+def t5_encoder_param_shapes(cfg: dict) -> Shapes:
+    """T5EncoderModel state_dict layout (transformers/models/t5/modeling_t5.py; built at models.py:98-100)."""
+    d, inner, ff = cfg["d_model"], cfg["num_heads"] * cfg["d_kv"], cfg["d_ff"]
+    s: Shapes = OrderedDict()
+    s["shared.weight"] = (cfg["vocab_size"], d)
+    for i in range(cfg["num_layers"]):
+        p = f"encoder.block.{i}.layer."
+        for n in ("q", "k", "v"):
+            s[p + f"0.SelfAttention.{n}.weight"] = (inner, d)
+        s[p + "0.SelfAttention.o.weight"] = (d, inner)
+        if i == 0:
+            s[p + "0.SelfAttention.relative_attention_bias.weight"] = (cfg["relative_attention_num_buckets"],
+                                                                      cfg["num_heads"])
+        s[p + "0.layer_norm.weight"] = (d,)
+        s[p + "1.DenseReluDense.wi_0.weight"] = (ff, d)
+        s[p + "1.DenseReluDense.wi_1.weight"] = (ff, d)
+        s[p + "1.DenseReluDense.wo.weight"] = (d, ff)
+        s[p + "1.layer_norm.weight"] = (d,)
+    s["encoder.final_layer_norm.weight"] = (d,)
+    return s
+
+
 def synth_tensor(key: str, shape, seed: int = 0) -> torch.Tensor:
     g = torch.Generator(device="cpu")
     g.manual_seed((zlib.crc32(key.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
     leaf = key.rsplit(".", 1)[-1]
-    is_norm = any(t in key for t in (".norm", "norm_out", "conv_norm_out")) and len(shape) == 1
+    is_norm = any(t in key for t in (".norm", "norm_out", "conv_norm_out", "layer_norm")) and len(shape) == 1
+    if key == "shared.weight":                       # token embeddings: unit scale, like the T5 initialiser
+        return torch.randn(shape, generator=g)
+    if key.endswith("SelfAttention.q.weight"):       # T5 has no 1/sqrt(d_kv) in the scores: fold it into q as T5's init does
+        return torch.randn(shape, generator=g) / math.sqrt(shape[1] * 64)
     if is_norm:
         if leaf == "weight":
             return 1.0 + 0.1 * torch.randn(shape, generator=g)

@@ -119,3 +119,33 @@ def test_no_cpu_fallback():
     d.set_timesteps(10)
     with pytest.raises(L.TangoB200Error):
         d.step(torch.zeros(1, 8, 4, 4), 990, torch.zeros(1, 8, 4, 4))
+
+
+def test_t5_relative_bucket_table_matches_oracle():
+    from oracle import t5 as ot5
+    from tango_b200.t5 import relative_position_buckets
+    for Lt in (1, 2, 10, 64, 150, 512):
+        pos = torch.arange(Lt)
+        want = ot5.relative_position_bucket(pos[None, :] - pos[:, None], 32, 128)      # [query, key]
+        tab = relative_position_buckets(Lt, 32, 128)                                     # index key - query + L - 1
+        got = tab[(pos[None, :] - pos[:, None]) + Lt - 1]
+        assert torch.equal(got, want)
+
+
+def test_t5_param_shapes_and_state_dict_contract():
+    from tango_b200 import synth
+    from tango_b200.t5 import T5EncoderModel
+    shp = synth.t5_encoder_param_shapes(synth.FLAN_T5_LARGE_CONFIG)
+    n = sum(int(torch.tensor(s).prod()) for s in shp.values())
+    assert n == 341_231_104                       # google/flan-t5-large encoder + shared embedding
+    m = T5EncoderModel.from_config(synth.TINY_T5_CONFIG)
+    sd = synth.synth_state_dict(synth.t5_encoder_param_shapes(synth.TINY_T5_CONFIG), 0)
+    sd2 = dict(sd)
+    sd2["encoder.embed_tokens.weight"] = sd2.pop("shared.weight")      # checkpoints may carry only the tied copy
+    assert not m.load_state_dict(sd2).missing_keys
+    bad = dict(sd)
+    bad.pop("encoder.final_layer_norm.weight")
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad)
+    with pytest.raises(Exception):                # no CPU fallback
+        m(torch.zeros(1, 4, dtype=torch.long))

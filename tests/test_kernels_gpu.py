@@ -351,3 +351,74 @@ def test_small_fp32_ops(cuda):
     import numpy as np
     expect = (torch.tanh(xw).cpu().numpy() * 32768).astype("int16")
     assert np.array_equal(wi.cpu().numpy(), expect)
+
+
+# ------------------------------------------------------------------------------------------------ T5 front-end kernels
+@pytest.mark.parametrize("Cc", [128, 1024, 2048])
+def test_rmsnorm(cuda, Cc):
+    rows = 333
+    g = torch.Generator(device="cpu").manual_seed(Cc)
+    x = (torch.randn(rows, Cc, generator=g) * 3 + 0.5).to(cuda)
+    gamma = torch.randn(Cc, generator=g).to(cuda)
+    y = torch.empty(rows, 2 * Cc, device=cuda, dtype=torch.bfloat16)
+    yf = torch.empty(rows, Cc, device=cuda)
+    L.rmsnorm(x, gamma, 1e-6, y, split_off=Cc, y_f32=yf)
+    ref = gamma * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6))
+    torch.cuda.synchronize()
+    assert rel_err(yf, ref) < 1e-6
+    assert rel_err(y[:, :Cc].float() + y[:, Cc:].float(), ref) < 1e-5
+
+
+def test_gather_rows(cuda):
+    g = torch.Generator(device="cpu").manual_seed(5)
+    table = torch.randn(97, 128, generator=g).to(cuda)
+    ids = torch.randint(0, 97, (41,), generator=g).to(cuda)
+    out = torch.empty(41, 128, device=cuda)
+    L.gather_rows(table, ids, out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, table[ids])
+
+
+@pytest.mark.parametrize("B,heads,Lt", [(2, 2, 10), (3, 16, 64), (1, 4, 150), (1, 2, 513)])
+def test_rel_attention(cuda, B, heads, Lt):
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + Lt)
+    inner = heads * 64
+    qkv = torch.randn(B * Lt, 3 * inner, generator=g)
+    qkv[:, :inner] *= 0.3
+    relbias = torch.randn(heads, 2 * Lt - 1, generator=g)
+    mask = torch.ones(B, Lt)
+    mask[0, max(1, Lt - 3):] = 0
+    kbias = (1.0 - mask) * torch.finfo(torch.float32).min
+    out = torch.empty(B * Lt, 2 * inner, device=cuda, dtype=torch.bfloat16)
+    L.rel_attention(qkv.to(cuda), relbias.to(cuda), kbias.to(cuda), out, batch=B, heads=heads, L=Lt, q_col0=0,
+                    k_col0=inner, v_col0=2 * inner, split_off=inner)
+    q, k, v = (qkv[:, i * inner:(i + 1) * inner].view(B, Lt, heads, 64).transpose(1, 2) for i in range(3))
+    pos = torch.arange(Lt)
+    bias = relbias[:, (pos[None, :] - pos[:, None]) + Lt - 1][None] + kbias[:, None, None, :]
+    ref = ((q @ k.transpose(-1, -2) + bias).softmax(-1) @ v).transpose(1, 2).reshape(B * Lt, inner)
+    torch.cuda.synchronize()
+    got = out[:, :inner].float() + out[:, inner:].float()
+    assert rel_err(got.cpu(), ref) < 2e-5
+
+
+def test_gated_tanh_gelu_epilogue(cuda):
+    M, Cc, inner = 70, 128, 256
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = torch.randn(M, Cc, generator=g).to(cuda)
+    w = (torch.randn(2 * inner, Cc, generator=g) * 2 / math.sqrt(Cc)).to(cuda)     # rows: [hidden | gate]
+    pc = ops.PackedConv(w, None, split=False, device=cuda, geglu_bn=256, geglu_tanh=True)
+    xb = bf(x)
+    ob = torch.empty(M, inner, device=cuda, dtype=torch.bfloat16)
+    ops.run_linear(pc, xb, out_bf16=ob)
+    proj = xb.float() @ bf(w).float().t()
+    ref = proj[:, :inner] * F.gelu(proj[:, inner:], approximate="tanh")
+    torch.cuda.synchronize()
+    assert rel_err(ob, ref) < 5e-3
+    # split (parity) mode: ~fp32 accuracy
+    pcs = ops.PackedConv(w, None, split=True, device=cuda, geglu_bn=256, geglu_tanh=True)
+    obs = torch.empty(M, 2 * inner, device=cuda, dtype=torch.bfloat16)
+    ops.run_linear(pcs, to_split(x), out_bf16=obs)
+    proj = x @ w.t()
+    ref = proj[:, :inner] * F.gelu(proj[:, inner:], approximate="tanh")
+    torch.cuda.synchronize()
+    assert rel_err(obs[:, :inner].float() + obs[:, inner:].float(), ref) < 5e-5

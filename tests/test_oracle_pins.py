@@ -140,3 +140,25 @@ def test_tiny_inference_golden():
     lat = opipe.inference(sd, cfg, o, torch.from_numpy(gd["embeds"]), torch.from_numpy(gd["mask"]), 4, 3.0,
                           torch.from_numpy(gd["lat0"]), noises)
     assert np.abs(lat.numpy() - gd["latents"]).max() < 2e-4
+
+
+def test_tiny_t5_golden():
+    """oracle/t5.py against outputs of transformers.T5EncoderModel (tests/golden/tiny_t5.npz, oracle/make_golden_t5.py)."""
+    from oracle import t5 as ot5
+    gd = gold("tiny_t5.npz")
+    cfg = synth.TINY_T5_CONFIG
+    assert cfg == ot5.TINY_T5_CONFIG
+    sd = synth.synth_state_dict(synth.t5_encoder_param_shapes(cfg), seed=0)
+    out = ot5.t5_encoder(sd, cfg, torch.from_numpy(gd["ids"]), torch.from_numpy(gd["mask"]))
+    assert np.abs(out.numpy() - gd["out"]).max() < 2e-5
+    out = ot5.t5_encoder(sd, cfg, torch.from_numpy(gd["ids_long"]), torch.from_numpy(gd["mask_long"]))
+    assert np.abs(out.numpy() - gd["out_long"]).max() < 2e-5
+
+
+def test_t5_bucket_known_answers():
+    """Bucket layout of the bidirectional relative attention (32 buckets, max distance 128): exact offsets below 8,
+    logarithmic bins above, positive offsets shifted by 16, saturation at |offset| >= 128."""
+    from oracle import t5 as ot5
+    rel = torch.tensor([0, -1, -7, -8, -15, -16, -127, -128, -1000, 1, 7, 8, 127, 128, 1000])
+    b = ot5.relative_position_bucket(rel, 32, 128).tolist()
+    assert b == [0, 1, 7, 8, 9, 10, 15, 15, 15, 17, 23, 24, 31, 31, 31]

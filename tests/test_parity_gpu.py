@@ -192,3 +192,44 @@ def test_tiny_inference_ddim_no_cfg_vs_oracle(cuda):
     e = rel(lat, ref)
     print(f"tiny 3-step DDIM, no CFG (split): rel err vs oracle {e:.3e}")
     assert e < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ FLAN-T5 encoder
+@pytest.mark.parametrize("precision", ["split", "bf16"])
+def test_tiny_t5_encoder_vs_golden(cuda, precision):
+    """tango_b200.t5.T5EncoderModel against transformers.T5EncoderModel outputs (tests/golden/tiny_t5.npz)."""
+    from tango_b200.t5 import T5EncoderModel
+    gd = np.load(os.path.join(GOLD, "tiny_t5.npz"))
+    cfg = synth.TINY_T5_CONFIG
+    m = T5EncoderModel.from_config(cfg, precision=precision).to(cuda)
+    m.load_state_dict(synth.synth_state_dict(synth.t5_encoder_param_shapes(cfg), seed=0))
+    tol = {"split": 1e-4, "bf16": 2e-2}[precision]
+    for tag in ("", "_long"):
+        ids, mask = torch.from_numpy(gd["ids" + tag]).to(cuda), torch.from_numpy(gd["mask" + tag]).to(cuda)
+        out = m(input_ids=ids, attention_mask=mask)[0]
+        assert out.shape == gd["out" + tag].shape and out.dtype == torch.float32
+        e = rel(out, gd["out" + tag])
+        print(f"tiny T5 {precision}{tag}: rel err vs transformers golden {e:.3e}")
+        assert e < tol
+    with pytest.raises(IndexError):
+        m(input_ids=torch.full((1, 4), cfg["vocab_size"], device=cuda))
+
+
+def test_t5_encoder_large_shapes_vs_oracle(cuda):
+    """One FLAN-T5-large-width block stack (d_model 1024, 16 heads, d_ff 2816; 2 layers to keep the CPU oracle fast)."""
+    from oracle import t5 as ot5
+    from tango_b200.t5 import T5EncoderModel
+    cfg = dict(synth.FLAN_T5_LARGE_CONFIG, num_layers=2, vocab_size=512)
+    sd = synth.synth_state_dict(synth.t5_encoder_param_shapes(cfg), seed=3)
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, 512, (4, 24), generator=g)
+    mask = torch.ones(4, 24, dtype=torch.long)
+    mask[0, 1:] = 0
+    mask[2, 17:] = 0
+    want = ot5.t5_encoder(sd, cfg, ids, mask)
+    for precision, tol in (("split", 1e-4), ("bf16", 2e-2)):
+        m = T5EncoderModel.from_config(cfg, precision=precision).to(cuda)
+        m.load_state_dict(sd)
+        e = rel(m(ids.to(cuda), mask.to(cuda))[0], want)
+        print(f"T5-large-width {precision}: rel err vs oracle {e:.3e}")
+        assert e < tol
