@@ -347,6 +347,13 @@ def run_ours(args):
     roof["whole_path_tflops"] = whole
     roof["whole_path_frac"] = whole / pk["bf16_tflops_sustained"]
 
+    # ---------------- text-conditioning front-end: reported beside the metric, not inside it
+    # (BASELINE.json's metric excludes text encoding). FLAN-T5 encoder of the UNet's width, seeded random weights,
+    # `batch` prompts x `tokens` tokens (the "" prompt is cached by the pipeline and not re-encoded).
+    text = None
+    if rank == 0 and not args.no_text_encoder:
+        text = text_encoder_leg(args, dev)
+
     # ---------------- CPU baseline (oracle port) on a bounded sample, N = 1 only
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -359,11 +366,42 @@ def run_ours(args):
             "config": workload_config(args, world), "unet_step_ms": float(np.mean(unet_ms)),
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+    if text is not None:
+        line["text_encoder"] = text
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def text_encoder_leg(args, dev):
+    from tango_b200 import synth
+    from tango_b200.t5 import T5EncoderModel
+    cfg = synth.FLAN_T5_LARGE_CONFIG if args.unet == "base" else synth.FLAN_T5_XL_CONFIG
+    m = T5EncoderModel.from_config(cfg, precision=args.precision).to(dev)
+    m.load_state_dict(synth.synth_state_dict(synth.t5_encoder_param_shapes(cfg), 0))
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(2, cfg["vocab_size"], (args.batch, args.tokens), generator=g).to(dev)
+    mask = torch.ones(args.batch, args.tokens, dtype=torch.long, device=dev)
+    for _ in range(2):
+        m(ids, mask)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        m(ids, mask)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    rows, d, ff, inner = args.batch * args.tokens, cfg["d_model"], cfg["d_ff"], cfg["num_heads"] * cfg["d_kv"]
+    flops = cfg["num_layers"] * (2 * rows * (4 * d * inner + 3 * d * ff) + 4 * args.batch * cfg["num_heads"] * args.tokens ** 2 * 64)
+    del m
+    torch.cuda.empty_cache()
+    return {"model": ("flan-t5-large" if args.unet == "base" else "flan-t5-xl") + " encoder, seeded random weights",
+            "prompts": args.batch, "tokens": args.tokens, "ms": ms, "tflops": flops / (ms / 1e3) / 1e12,
+            "note": "eager launches (not graph-captured); outside the timed metric"}
 
 
 def cpu_baseline(args):
@@ -387,6 +425,7 @@ def main():
     ap.add_argument("--scheduler", default="ddim", choices=["ddim", "ddpm"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "split"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-text-encoder", action="store_true", help="skip the FLAN-T5 front-end timing leg")
     ap.add_argument("--latent-h", type=int, default=256, help="latent time frames: 256 = 10.24 s (reference), 768 = 30.7 s")
     ap.add_argument("--unet", default="base", choices=["base", "xl"])
     args = ap.parse_args()

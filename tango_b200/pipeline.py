@@ -10,8 +10,12 @@ same names, argument meaning, defaults and return types. What changes underneath
     per-step coefficient table, so there is no host sync inside the loop (the reference has two per step);
   * a prompt batch can be sharded over the GPUs of one box (tango_b200/parallel.py) — samples are independent.
 
-Text encoding (FLAN-T5) is the boundary input of the accelerated path: a Hugging Face T5 encoder
-is used when its weights are available locally; tests and the benchmark inject synthetic `prompt_embeds`.
+Text encoding: the FLAN-T5 encoder runs on the same kernels (tango_b200/t5.py) whenever its
+weights are present (`text_encoder.*` of pytorch_model_main.bin, or a local snapshot directory); the unconditional
+("") embedding is computed once per padded length and reused. Tokenisation stays on the host (AutoTokenizer from a
+local snapshot; a flagged stand-in tokenizer when SentencePiece data is not reachable). Without any encoder weights a
+flagged synthetic encoder supplies conditioning of the right shape; tests and the benchmark may also inject
+`prompt_embeds` directly.
 """
 from __future__ import annotations
 
@@ -28,6 +32,7 @@ from . import lib as L
 from . import parallel
 from . import synth
 from .schedulers import DDIMScheduler, DDPMScheduler
+from .t5 import T5EncoderModel
 from .unet import UNet2DConditionModel
 from .vae import AutoencoderKL
 
@@ -56,6 +61,47 @@ class SyntheticTextEncoder:
         return emb, mask
 
 
+class FallbackTokenizer:
+    """Stand-in for the FLAN-T5 SentencePiece tokenizer when its `spiece.model` is not reachable (offline box): words
+    are hashed into the vocabulary, EOS (id 1) is appended, pad id is 0 — the call signature and the padding /
+    truncation behaviour the reference relies on (models.py:131-133, 268-286) are kept, the ids themselves are NOT
+    T5's. Flagged `.synthetic`; with a real snapshot directory `AutoTokenizer` is used instead."""
+
+    synthetic = True
+    model_max_length = 512
+
+    def __init__(self, vocab_size: int):
+        self.vocab_size = vocab_size
+
+    def __call__(self, prompts, max_length=None, padding=True, truncation=True, return_tensors="pt"):
+        max_length = max_length or self.model_max_length
+        rows = []
+        for p in prompts:
+            ids = [2 + zlib.crc32(w.encode()) % (self.vocab_size - 2) for w in p.split()] + [1]
+            if truncation and len(ids) > max_length:
+                ids = ids[:max_length - 1] + [1]
+            rows.append(ids)
+        width = max_length if padding == "max_length" else max(len(r) for r in rows)
+        input_ids = torch.zeros(len(rows), width, dtype=torch.long)
+        mask = torch.zeros(len(rows), width, dtype=torch.long)
+        for i, r in enumerate(rows):
+            input_ids[i, :len(r)] = torch.tensor(r)
+            mask[i, :len(r)] = 1
+        return SimpleNamespace(input_ids=input_ids, attention_mask=mask)
+
+
+def t5_config_from_state_dict(te: dict) -> dict:
+    """Encoder hyper-parameters recovered from `text_encoder.*` tensor shapes (pytorch_model_main.bin carries no config)."""
+    emb = te["shared.weight"] if "shared.weight" in te else te["encoder.embed_tokens.weight"]
+    layers = 1 + max(int(k.split(".")[2]) for k in te if k.startswith("encoder.block."))
+    inner = te["encoder.block.0.layer.0.SelfAttention.q.weight"].shape[0]
+    buckets, heads = te["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"].shape
+    return {"vocab_size": emb.shape[0], "d_model": emb.shape[1], "d_kv": inner // heads, "num_heads": heads,
+            "d_ff": te["encoder.block.0.layer.1.DenseReluDense.wi_0.weight"].shape[0], "num_layers": layers,
+            "relative_attention_num_buckets": buckets, "relative_attention_max_distance": 128,
+            "layer_norm_epsilon": 1e-6, "feed_forward_proj": "gated-gelu"}
+
+
 class AudioDiffusion:
     """Inference half of /root/reference/models.py:AudioDiffusion (the training half, :105-208, is out of scope)."""
 
@@ -80,6 +126,7 @@ class AudioDiffusion:
         self.device = torch.device("cpu")
         self.tokenizer = None
         self.text_encoder = None
+        self._uncond_cache = {}
         self._state = {}
         self._temb_cache = {}
         self.last_step_ms: Optional[float] = None
@@ -102,21 +149,32 @@ class AudioDiffusion:
         unet_sd = {k[len("unet."):]: v for k, v in sd.items() if k.startswith("unet.")}
         self.unet.load_state_dict(unet_sd, strict=strict)
         te = {k[len("text_encoder."):]: v for k, v in sd.items() if k.startswith("text_encoder.")}
-        if te and self.text_encoder is not None and not getattr(self.text_encoder, "synthetic", False):
-            self.text_encoder.load_state_dict(te, strict=strict)
+        if te:
+            self.set_text_encoder_state_dict(te)
         return SimpleNamespace(missing_keys=[], unexpected_keys=[])
 
+    def set_text_encoder_state_dict(self, te: dict, config: Optional[dict] = None):
+        """Build the FLAN-T5 encoder (tango_b200.t5.T5EncoderModel, on the kernels) from `text_encoder.*` weights."""
+        self.text_encoder = T5EncoderModel.from_config(config or t5_config_from_state_dict(te),
+                                                       precision=self.precision).to(self.device)
+        self.text_encoder.load_state_dict(te, strict=False)
+        self._uncond_cache = {}
+
     def _ensure_text_encoder(self):
-        if self.text_encoder is not None:
-            return
+        """Tokenizer: AutoTokenizer from a local snapshot of `text_encoder_name`, else the flagged FallbackTokenizer.
+        Encoder: the one built from `text_encoder.*` weights (load_state_dict), else a local snapshot directory, else
+        the flagged SyntheticTextEncoder (no weights reachable offline)."""
         name = self.text_encoder_name or ""
-        try:
-            from transformers import AutoTokenizer, T5EncoderModel
-            self.tokenizer = AutoTokenizer.from_pretrained(name, local_files_only=True)
-            self.text_encoder = T5EncoderModel.from_pretrained(name, local_files_only=True).to(self.device).eval()
-        except Exception:
-            # offline and no local checkpoint: synthetic conditioning of the right shape (flagged `.synthetic`)
+        if self.text_encoder is None and os.path.isdir(name) and os.path.exists(os.path.join(name, "config.json")):
+            self.text_encoder = T5EncoderModel.from_pretrained(name, precision=self.precision).to(self.device)
+        if self.text_encoder is None:
             self.text_encoder = SyntheticTextEncoder(self.unet.config["cross_attention_dim"])
+        if self.tokenizer is None and not getattr(self.text_encoder, "synthetic", False):
+            try:
+                from transformers import AutoTokenizer
+                self.tokenizer = AutoTokenizer.from_pretrained(name, local_files_only=True)
+            except Exception:
+                self.tokenizer = FallbackTokenizer(self.text_encoder.cfg["vocab_size"])
 
     # ------------------------------------------------------------------------------------------ text (boundary input)
     def encode_text(self, prompt: List[str]):
@@ -144,11 +202,16 @@ class AudioDiffusion:
             ids, am = batch.input_ids.to(self.device), batch.attention_mask.to(self.device)
             with torch.no_grad():
                 emb = self.text_encoder(input_ids=ids, attention_mask=am)[0]
-            ub = self.tokenizer([""] * len(prompt), max_length=emb.shape[1], padding="max_length", truncation=True,
-                                return_tensors="pt")
-            uids, nam = ub.input_ids.to(self.device), ub.attention_mask.to(self.device)
-            with torch.no_grad():
-                nemb = self.text_encoder(input_ids=uids, attention_mask=nam)[0]
+            # the "" prompt encodes to the same tensor for every sample and call: run it once per padded length
+            key = int(emb.shape[1])
+            hit = self._uncond_cache.get(key)
+            if hit is None:
+                ub = self.tokenizer([""], max_length=key, padding="max_length", truncation=True, return_tensors="pt")
+                uids, uam = ub.input_ids.to(self.device), ub.attention_mask.to(self.device)
+                with torch.no_grad():
+                    hit = (self.text_encoder(input_ids=uids, attention_mask=uam)[0], uam)
+                self._uncond_cache[key] = hit
+            nemb, nam = hit[0].expand(len(prompt), -1, -1), hit[1].expand(len(prompt), -1)
         emb = emb.repeat_interleave(num_samples_per_prompt, 0)
         am = am.repeat_interleave(num_samples_per_prompt, 0)
         nemb = nemb.repeat_interleave(num_samples_per_prompt, 0)
@@ -302,8 +365,10 @@ class Tango:
 
     @classmethod
     def from_synthetic(cls, unet_config: Optional[dict] = None, device="cuda:0", precision: str = "bf16", seed: int = 0,
-                       scheduler: str = "ddpm"):
-        """Random-weight instance with the reference's architecture (no checkpoint is reachable offline)."""
+                       scheduler: str = "ddpm", t5_config: Optional[dict] = None):
+        """Random-weight instance with the reference's architecture (no checkpoint is reachable offline). With
+        `t5_config` (e.g. synth.FLAN_T5_LARGE_CONFIG) a random-weight FLAN-T5 encoder of that shape is attached too, so
+        prompts run through tokenizer -> T5 kernels -> UNet instead of the synthetic conditioning stand-in."""
         self = cls.__new__(cls)
         ucfg = dict(unet_config or synth.BASE_UNET_CONFIG)
         self._init_modules(dict(synth.VAE_CONFIG), {"scheduler_name": "stabilityai/stable-diffusion-2-1",
@@ -312,6 +377,11 @@ class Tango:
         self.vae.load_state_dict(synth.synth_state_dict(synth.vae_decoder_param_shapes(), seed))
         if scheduler == "ddim":
             self.scheduler = DDIMScheduler.from_pretrained(None)
+        if t5_config is not None:
+            if t5_config["d_model"] != ucfg["cross_attention_dim"]:
+                raise ValueError("t5_config['d_model'] must equal the UNet's cross_attention_dim")
+            self.model.set_text_encoder_state_dict(
+                synth.synth_state_dict(synth.t5_encoder_param_shapes(t5_config), seed), config=t5_config)
         return self
 
     def chunks(self, lst, n):

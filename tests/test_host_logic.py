@@ -149,3 +149,27 @@ def test_t5_param_shapes_and_state_dict_contract():
         m.load_state_dict(bad)
     with pytest.raises(Exception):                # no CPU fallback
         m(torch.zeros(1, 4, dtype=torch.long))
+
+
+def test_fallback_tokenizer_padding_and_truncation():
+    """The call conventions models.py:131-133 / :268-286 rely on: padding=True pads to the longest prompt,
+    padding="max_length" to max_length, EOS closes every row, the empty prompt is a lone EOS."""
+    from tango_b200.pipeline import FallbackTokenizer
+    tok = FallbackTokenizer(100)
+    b = tok(["a b c", "a"], max_length=tok.model_max_length, padding=True, truncation=True, return_tensors="pt")
+    assert b.input_ids.shape == (2, 4) and b.attention_mask.tolist() == [[1, 1, 1, 1], [1, 1, 0, 0]]
+    assert b.input_ids[0, 3] == 1 and b.input_ids[1, 1] == 1 and b.input_ids[1, 2] == 0
+    assert int(b.input_ids[0, 0]) == int(b.input_ids[1, 0]) >= 2            # same word, same id, never pad/EOS
+    u = tok([""], max_length=4, padding="max_length", truncation=True, return_tensors="pt")
+    assert u.input_ids.tolist() == [[1, 0, 0, 0]] and u.attention_mask.tolist() == [[1, 0, 0, 0]]
+    t = tok(["w " * 50], max_length=8, padding=True, truncation=True)
+    assert t.input_ids.shape == (1, 8) and t.input_ids[0, -1] == 1
+
+
+def test_t5_config_recovered_from_state_dict():
+    from tango_b200 import synth
+    from tango_b200.pipeline import t5_config_from_state_dict
+    cfg = dict(synth.FLAN_T5_LARGE_CONFIG, num_layers=2, vocab_size=64)
+    shapes = synth.t5_encoder_param_shapes(cfg)
+    te = {k: torch.empty(s, device="meta") for k, s in shapes.items()}
+    assert t5_config_from_state_dict(te) == cfg

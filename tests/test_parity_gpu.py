@@ -233,3 +233,35 @@ def test_t5_encoder_large_shapes_vs_oracle(cuda):
         e = rel(m(ids.to(cuda), mask.to(cuda))[0], want)
         print(f"T5-large-width {precision}: rel err vs oracle {e:.3e}")
         assert e < tol
+
+
+def test_prompts_through_tokenizer_t5_and_unet(cuda):
+    """encode_text_classifier_free (models.py:266-305) with the T5 encoder on the kernels, then a short generation."""
+    from oracle import t5 as ot5
+    cfg = synth.TINY_T5_CONFIG
+    t = Tango.from_synthetic(synth.TINY_UNET_CONFIG, device=cuda, precision="split", t5_config=cfg)
+    prompts = ["a dog barking", "rain on a tin roof while a train passes"]
+    pe, pm = t.model.encode_text_classifier_free(prompts, 2)
+    tok = t.model.tokenizer
+    assert getattr(tok, "synthetic", False)                      # no SentencePiece data on this box
+    sd = synth.synth_state_dict(synth.t5_encoder_param_shapes(cfg), 0)
+    b = tok(prompts, max_length=tok.model_max_length, padding=True, truncation=True, return_tensors="pt")
+    emb = ot5.t5_encoder(sd, cfg, b.input_ids, b.attention_mask)
+    ub = tok([""] * len(prompts), max_length=emb.shape[1], padding="max_length", truncation=True, return_tensors="pt")
+    nemb = ot5.t5_encoder(sd, cfg, ub.input_ids, ub.attention_mask)
+    want = torch.cat([nemb.repeat_interleave(2, 0), emb.repeat_interleave(2, 0)])
+    wmask = torch.cat([ub.attention_mask.repeat_interleave(2, 0), b.attention_mask.repeat_interleave(2, 0)]) == 1
+    assert pe.shape == want.shape and torch.equal(pm.cpu(), wmask)
+    assert rel(pe, want) < 1e-4
+    pe2, _ = t.model.encode_text_classifier_free(prompts, 2)     # second call reuses the cached "" embedding
+    assert torch.equal(pe, pe2)
+    lat = t.model.inference(prompts, t.scheduler, 2, 3.0, 1, latent_shape=(32, 16))
+    assert lat.shape == (2, 8, 32, 16) and torch.isfinite(lat).all()
+    # same latents when the embeddings are injected instead of encoded
+    g = torch.Generator(device=cuda).manual_seed(7)
+    a = t.model.inference(prompts, t.scheduler, 2, 3.0, 1, latent_shape=(32, 16), generator=g)
+    pe1, pm1 = t.model.encode_text_classifier_free(prompts, 1)
+    g = torch.Generator(device=cuda).manual_seed(7)
+    b2 = t.model.inference(prompts, t.scheduler, 2, 3.0, 1, latent_shape=(32, 16), generator=g, prompt_embeds=pe1,
+                           boolean_prompt_mask=pm1)
+    assert rel(a, b2) < 1e-4
