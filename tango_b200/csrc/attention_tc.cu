@@ -482,21 +482,27 @@ attention_sub_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_cons
           tma_load_3d(sV + buf * Cfg::KV_BYTES + s * AT_CHUNK, &vmap, &bar_v[buf],
                       p.v_col0 + s * p.v_lo_off + head * AT_D, tile * AT_BN, b);
       };
+      // Descriptors are built once: the issuer is a single serial instruction stream on the critical path of every
+      // hand-over, so per-issue work is reduced to a few adds (smem offsets enter the 16-byte address field directly).
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(AT_BM, SUB, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BM, AT_D, 0, 1);
+      const uint64_t qdesc0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t kdesc0 = umma_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t vdesc0 = umma_desc_sw128(smem_u32(sV), 1024, 1024);
+      const uint64_t pdesc0 = umma_desc_sw128(smem_u32(sP), 16, 1024);
+      constexpr int NT = (NSPLIT == 1) ? 1 : 3;
       // S[g & 1] = Q K_g^T over the 64 keys of sub-tile g (hi*hi [+ lo*hi + hi*lo])
       auto issue_qk = [&](int g) {
         const int buf = (g >> 1) % NB, h = g & 1;
-        constexpr uint32_t idesc = umma_idesc_bf16(AT_BM, SUB, 0, 0);
-        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + buf * Cfg::KV_BYTES) + h * HALF_BYTES;
-        constexpr int NT = (NSPLIT == 1) ? 1 : 3;
+        const uint64_t kd = kdesc0 + static_cast<uint64_t>((buf * Cfg::KV_BYTES + h * HALF_BYTES) >> 4);
         const int qsel[3] = {0, 1, 0}, ksel[3] = {0, 0, 1};
         uint32_t acc = 0;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-          const uint64_t adesc = umma_desc_sw128(qa + qsel[t] * AT_CHUNK, 16, 1024);
-          const uint64_t bdesc = umma_desc_sw128(ka + ksel[t] * AT_CHUNK, 16, 1024);
 #pragma unroll
           for (int k = 0; k < AT_D / 16; ++k) {
-            umma_bf16(tm_s + h * SUB, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+            umma_bf16(tm_s + h * SUB, qdesc0 + static_cast<uint64_t>((qsel[t] * AT_CHUNK) >> 4) + 2 * k,
+                      kd + static_cast<uint64_t>((ksel[t] * AT_CHUNK) >> 4) + 2 * k, idesc_qk, acc);
             acc = 1;
           }
         }
@@ -505,9 +511,8 @@ attention_sub_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_cons
       // O (+)= P_g V_g   (A = P chunk g&1, K-major; B = V rows [64 h, 64 h + 16 nk16), MN-major: 16 keys = 2048 B)
       auto issue_pv = [&](int g, uint32_t accumulate, int nk16) {
         const int buf = (g >> 1) % NB, h = g & 1;
-        constexpr uint32_t idesc = umma_idesc_bf16(AT_BM, AT_D, 0, 1);
-        const uint32_t pa = smem_u32(sP) + h * AT_CHUNK, va = smem_u32(sV + buf * Cfg::KV_BYTES) + h * HALF_BYTES;
-        constexpr int NT = (NSPLIT == 1) ? 1 : 3;
+        const uint64_t vd = vdesc0 + static_cast<uint64_t>((buf * Cfg::KV_BYTES + h * HALF_BYTES) >> 4);
+        const uint64_t pd = pdesc0 + static_cast<uint64_t>((h * AT_CHUNK) >> 4);
         const int psel[3] = {0, 1, 0}, vsel[3] = {0, 0, 1};
         uint32_t acc = accumulate;
 #pragma unroll
@@ -515,13 +520,9 @@ attention_sub_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_cons
 #pragma unroll
           for (int k = 0; k < SUB / 16; ++k) {
             if (k >= nk16) break;  // keys beyond the written P columns (short last sub-tile)
-            const uint64_t bdesc = umma_desc_sw128(va + vsel[t] * AT_CHUNK + k * 2048, 1024, 1024);
-            if (P_TMEM) {
-              umma_bf16_ts(tm_o, tm_p + psel[t] * 64 + h * 32 + 8 * k, bdesc, idesc, acc);
-            } else {
-              const uint64_t adesc = umma_desc_sw128(pa + psel[t] * 2 * AT_CHUNK, 16, 1024) + 2 * k;
-              umma_bf16(tm_o, adesc, bdesc, idesc, acc);
-            }
+            const uint64_t bdesc = vd + static_cast<uint64_t>((vsel[t] * AT_CHUNK + k * 2048) >> 4);
+            if (P_TMEM) umma_bf16_ts(tm_o, tm_p + psel[t] * 64 + h * 32 + 8 * k, bdesc, idesc_pv, acc);
+            else umma_bf16(tm_o, pd + static_cast<uint64_t>((psel[t] * 2 * AT_CHUNK) >> 4) + 2 * k, bdesc, idesc_pv, acc);
             acc = 1;
           }
         }
@@ -543,14 +544,15 @@ attention_sub_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_cons
         const int kv0 = g * SUB;
         const bool tail = (p.kbias != nullptr) || (kv0 + SUB > p.Lk);
         const int ncols = tail ? min(SUB, ((p.Lk - kv0) + 31) & ~31) : SUB;   // same rule as the softmax warps
+        if (h == 0) mbar_wait(&bar_v[T % NB], (T / NB) & 1);    // first use of V tile T (h == 1 reuses it)
         mbar_wait(&bar_p[h], T & 1);     // P_g written (and fenced / stored), S_g fully read
-        mbar_wait(&bar_v[T % NB], (T / NB) & 1);
         tc_fence_after();
         issue_pv(g, g > 0 ? 1u : 0u, ncols / 16);
         if (g + 2 < n_sub) {
-          const int T2 = (g + 2) >> 1;
-          mbar_wait(&bar_k[T2 % NB], (T2 / NB) & 1);
-          tc_fence_after();
+          if (h == 0) {                  // first use of K tile T + 1
+            mbar_wait(&bar_k[(T + 1) % NB], ((T + 1) / NB) & 1);
+            tc_fence_after();
+          }
           issue_qk(g + 2);       // commits bar_s[h] after P V_g and Q K_{g+2}^T
         }
         if (h == 1) {
@@ -576,11 +578,23 @@ attention_sub_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_cons
     uint8_t* prow_base = sP + r * 128;
     const int rsw = r & 7;
 
-    for (int g = 0; g < n_sub; ++g) {
-      const int h = g & 1, T = g >> 1;
+    // S of sub-tile g is requested (tcgen05.ld of both 32-column chunks) while P of sub-tile g-1 is still being stored
+    // and handed over, so the TMEM round trips of consecutive sub-tiles overlap. The loads are waited for before the
+    // loop back-edge: the registers must hold the data before the compiler may move them.
+    uint32_t va[32], vb[32];
+    auto request_s = [&](int g) {
+      const int h = g & 1;
       __syncwarp();
-      mbar_wait(&bar_s[h], T & 1);   // S_g complete; in-order tensor pipe => P V_{g-2} complete as well (P half free)
+      mbar_wait(&bar_s[h], (g >> 1) & 1);   // S_g complete; in-order tensor pipe => P V_{g-2} complete (P half free)
       tc_fence_after();
+      const int left = p.Lk - g * SUB;      // > 0
+      tmem_ld32(ts + h * SUB, va);
+      if (left > 32) tmem_ld32(ts + h * SUB + 32, vb);
+    };
+    request_s(0);
+    tmem_ld_wait();
+    for (int g = 0; g < n_sub; ++g) {
+      const int h = g & 1;
       const int kv0 = g * SUB;
       const bool tail = (kb != nullptr) || (kv0 + SUB > p.Lk);
       // columns actually processed in this sub-tile (multiple of 32); P columns beyond are never written nor multiplied
@@ -597,13 +611,13 @@ attention_sub_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_cons
       }
       const uint32_t tsh = ts + h * SUB;
       if (g == 0) {
-        // explicit maximum pass for the very first sub-tile (no reference yet)
+        // explicit maximum for the very first sub-tile (no reference yet), from the registers already loaded
         float m_tile = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < ncols; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(tsh + c, v);
-          tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          if (cc == 1 && ncols <= 32) break;
+          const int c = 32 * cc;
+          const uint32_t* v = cc ? vb : va;
           float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
           if (!tail) {
 #pragma unroll
@@ -634,12 +648,11 @@ attention_sub_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_cons
         float xmax = -INFINITY;
         lsum = 0.f;
         uint8_t* prow = prow_base + h * AT_CHUNK;
-        // both 32-column chunks of the sub-tile are requested before the first one is consumed: one exposed TMEM
-        // latency per sub-tile instead of two
-        uint32_t va[32], vb[32];
-        tmem_ld32(tsh, va);
-        if (ncols > 32) tmem_ld32(tsh + 32, vb);
-        tmem_ld_wait();
+        if (round == 1) {   // the recompute after a rescale reads S_g again
+          tmem_ld32(tsh, va);
+          if (ncols > 32) tmem_ld32(tsh + 32, vb);
+          tmem_ld_wait();
+        }
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           if (cc == 1 && ncols <= 32) break;
@@ -737,10 +750,12 @@ attention_sub_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_cons
       l_run += lsum;
       // hand-over: P visible to the tensor core (smem: generic -> async proxy fence; TMEM: stores complete);
       // S reads / O rescales are done
+      if (g + 1 < n_sub) request_s(g + 1);
       if (P_TMEM) tmem_st_wait();
       else fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&bar_p[h]);
+      tmem_ld_wait();
     }
 
     // ---- finalize: O / l -> bf16 (hi/lo)
