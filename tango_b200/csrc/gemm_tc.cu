@@ -37,6 +37,7 @@ struct GemmKernelParams {
   int m_tiles, n_tiles;
   int Ncols;
   int n_groups, total_kiters;
+  int ksplit;    // 1, or 2: two CTAs share an output tile, each reduces half of the K iterations and red.adds fp32 partials
   KGroupDev g[TNG_MAX_KGROUPS];
   // epilogue
   const float* bias;
@@ -354,6 +355,58 @@ __device__ __noinline__ void epi_tile_generic(const GemmKernelParams& p, float* 
   }
 }
 
+// Split-K epilogue: this CTA holds the partial sum over its half of K. out (+)= alpha * (partial [+ bias + rowvec + res
+// for the first half only]) with fp32 red.adds into an output the host zeroed beforehand. With exactly two partials
+// per element the result does not depend on their order (0 + a + b, fp32 addition commutes), so runs stay
+// reproducible. Used for under-filled launches with a long reduction (the 32x2 level of the UNet): the epilogue is
+// small next to the main loop, so this is the simple row-slot form.
+template <int BN>
+__device__ __noinline__ void epi_tile_splitk(const GemmKernelParams& p, float* st, long long row_base, int n0, int rpi,
+                                             int nvalid, int sp, uint32_t taddr, int tn, int lane, int ew, int hf) {
+  const int cg = lane & 7, rsub = lane >> 3;
+#pragma unroll 1
+  for (int c = hf * 32; c < BN; c += 64) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c, v);
+    tmem_ld_wait();
+    __syncwarp();
+    epi_stage(st, lane, v);
+    __syncwarp();
+    const int col = tn * BN + c + 4 * cg;
+    const bool col_ok = col < p.Ncols;   // Ncols % 4 == 0 (checked on the host)
+    float4 add4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col_ok && sp == 0 && p.bias) add4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      const int rr = ew * 32 + 4 * i + rsub;
+      if (!col_ok || rr >= nvalid) continue;
+      const long long row = row_base + rr;
+      float4 a = *reinterpret_cast<const float4*>(st + (4 * i + rsub) * 32 + ((cg ^ ((4 * i + rsub) & 7)) << 2));
+      if (sp == 0) {
+        a.x += add4.x; a.y += add4.y; a.z += add4.z; a.w += add4.w;
+        if (p.rowvec) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(n0 + rr / rpi) * p.rowvec_ld + col));
+          a.x += r4.x; a.y += r4.y; a.z += r4.z; a.w += r4.w;
+        }
+        if (p.res) {
+          if (p.res_bf16) {
+            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + row * p.ldr + col);
+            const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            a.x += f0.x; a.y += f0.y; a.z += f1.x; a.w += f1.y;
+          } else {
+            const float4 r4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + row * p.ldr + col);
+            a.x += r4.x; a.y += r4.y; a.z += r4.z; a.w += r4.w;
+          }
+        }
+      }
+      a.x *= p.alpha; a.y *= p.alpha; a.z *= p.alpha; a.w *= p.alpha;
+      float* op = p.out_f32 + row * p.ld_f32 + col;
+      atomicAdd(op, a.x); atomicAdd(op + 1, a.y); atomicAdd(op + 2, a.z); atomicAdd(op + 3, a.w);
+    }
+  }
+}
+
 // GEGLU: columns [0, BN/2) of the tile are "hidden", [BN/2, BN) the matching "gate" (weights interleaved on the
 // host). out[:, tn*BN/2 + j] = (hid + b) * gelu_erf(gate + b'). Rows r0 + 4i (consecutive-row tiles); rows >= nvalid
 // are skipped.
@@ -486,7 +539,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
 
   // work items: (pair of adjacent M tiles) x N tile; CTA `crank` of the cluster takes M tile 2*mp + crank
   const int m_groups = (p.m_tiles + CLUSTER - 1) / CLUSTER;
-  const int total_tiles = m_groups * p.n_tiles;
+  const int total_tiles = m_groups * p.n_tiles * p.ksplit;   // split-K: consecutive work items = the K halves of one tile
   const int work0 = blockIdx.x / CLUSTER, work_stride = gridDim.x / CLUSTER;
 
   if (warp == 0 && lane == 0) {
@@ -494,15 +547,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = work0; tile < total_tiles; tile += work_stride) {
-      const int tm = (tile / p.n_tiles) * CLUSTER + crank, tn = tile % p.n_tiles;
+      const int sp = tile % p.ksplit, t2 = tile / p.ksplit;
+      const int tm = (t2 / p.n_tiles) * CLUSTER + crank, tn = t2 % p.n_tiles;
       const int tw = tm % p.tiles_w;
       const int th = (tm / p.tiles_w) % p.tiles_h;
       const int tb = tm / (p.tiles_w * p.tiles_h);
       const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tb * p.bn;
+      // flat K-iteration range of this work item (all of them unless split-K)
+      const int k_lo = sp * p.total_kiters / p.ksplit, k_hi = (sp + 1) * p.total_kiters / p.ksplit;
+      int kbase = 0;
       for (int gi = 0; gi < p.n_groups; ++gi) {
         const KGroupDev g = p.g[gi];
         const CUtensorMap* am = g.view == 0 ? &amap0 : g.view == 1 ? &amap1 : g.view == 2 ? &amap2 : &amap3;
-        for (int kb = 0; kb < g.nkb; ++kb) {
+        const int kb_lo = max(0, k_lo - kbase), kb_hi = min(g.nkb, k_hi - kbase);
+        kbase += g.nkb;
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (PAIR) {
             // both CTAs load into their own smem; all bytes are credited to the LEADER's full barrier
@@ -547,7 +606,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
-      for (int ki = 0; ki < p.total_kiters; ++ki) {
+      const int sp = tile % p.ksplit;
+      const int nk = (sp + 1) * p.total_kiters / p.ksplit - sp * p.total_kiters / p.ksplit;
+      for (int ki = 0; ki < nk; ++ki) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * A_TILE_BYTES), 16, 1024);
@@ -576,7 +637,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     const bool geglu = (p.act == TNG_ACT_GEGLU || p.act == TNG_ACT_GEGLU_TANH);
     int it = 0;
     for (int tile = work0; tile < total_tiles; tile += work_stride, ++it) {
-      const int tm = (tile / p.n_tiles) * CLUSTER + crank, tn = tile % p.n_tiles;
+      const int sp = tile % p.ksplit, t2 = tile / p.ksplit;
+      const int tm = (t2 / p.n_tiles) * CLUSTER + crank, tn = t2 % p.n_tiles;
       const int tw = tm % p.tiles_w;
       const int th = (tm / p.tiles_w) % p.tiles_h;
       const int tb = tm / (p.tiles_w * p.tiles_h);
@@ -606,6 +668,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
           tmem_ld_wait();
           if (v[0] == 0x7fc12345u && v[7] == 0x12345u) st[lane] = __uint_as_float(v[3]);
         }
+      } else if (p.ksplit > 1) {
+        epi_tile_splitk<BN>(p, st, row_base, n0, rpi, nvalid, sp, taddr, tn, lane, ew, hf);
       } else if (geglu) {
         // slot i of this lane is row ew*32 + rsub + 4i; rows below nvalid are valid
         if constexpr (BN == 128 || BN == 256) {   // the host only selects these N tiles for GEGLU
@@ -675,7 +739,7 @@ static int launch_gemm_cl(const CUtensorMap* am, const CUtensorMap& bm, const Ge
     if (e != cudaSuccess) return set_error(TNG_ECUDA, "cudaFuncSetAttribute(gemm_tc<%d,%d>): %s", BN, CL, cudaGetErrorString(e));
     attr_set = true;
   }
-  const int work = ((p.m_tiles + CLUSTER - 1) / CLUSTER) * p.n_tiles;
+  const int work = ((p.m_tiles + CLUSTER - 1) / CLUSTER) * p.n_tiles * p.ksplit;
   const int slots = num_sms() / CLUSTER;
   const int grid = (work < slots ? work : slots) * CLUSTER;
   cudaLaunchConfig_t cfg;
@@ -742,6 +806,7 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   p.Ncols = (int)d->Ncols;
 
   int bn_tile = d->block_n;
+  int ksplit = 1;
   if (d->act == TNG_ACT_GEGLU || d->act == TNG_ACT_GEGLU_TANH) {
     if (bn_tile == 0) bn_tile = (d->Ncols % 256 == 0) ? 256 : 128;
     if ((bn_tile != 128 && bn_tile != 256) || d->Ncols % bn_tile != 0 || !d->out_bf16 || d->out_f32 || d->res ||
@@ -755,15 +820,24 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
     else if (N % 256 == 0 && (long long)p.m_tiles * (N / 256) >= 2 * num_sms()) bn_tile = 256;
     else if (N % 160 == 0) {
       bn_tile = 160;
-      // under-filled launches (e.g. the 32x2 level of the UNet: 8 M tiles): more, smaller N tiles keep more SMs busy
-      if (N % 128 == 0 && (long long)p.m_tiles * (N / 160) * 2 <= num_sms() && (long long)p.m_tiles * (N / 128) <= num_sms())
-        bn_tile = 128;
+      // under-filled launches (e.g. the 32x2 level of the UNet: 8 M tiles)
+      if ((long long)p.m_tiles * (N / 160) * 2 <= num_sms()) {
+        static int splitk = -1;   // TNG_GEMM_SPLITK=0 disables (A/B measurements)
+        if (splitk < 0) { const char* e = getenv("TNG_GEMM_SPLITK"); splitk = e ? atoi(e) : 1; }
+        long long kit = 0;
+        for (int i = 0; i < d->n_groups; ++i) kit += d->g[i].nkb;
+        const bool can_split = splitk && d->out_f32 && !d->out_bf16 && !d->accumulate && d->act == TNG_ACT_NONE &&
+                               d->res != d->out_f32 && kit >= 32 && d->Ncols % 4 == 0;
+        if (can_split) ksplit = 2;   // two CTAs per output tile, each reduces half of K (long reductions only)
+        else if (N % 128 == 0 && (long long)p.m_tiles * (N / 128) <= num_sms()) bn_tile = 128;  // more, smaller N tiles
+      }
     }
     else if (N % 128 == 0) bn_tile = 128;
     else if (N % 64 == 0 && N < 256) bn_tile = 64;
     else bn_tile = 128;
   }
   p.n_tiles = (int)((d->Ncols + bn_tile - 1) / bn_tile);
+  p.ksplit = ksplit;
 
   p.n_groups = d->n_groups;
   p.total_kiters = 0;
@@ -815,6 +889,8 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
     if (force < 0) { const char* e = getenv("TNG_GEMM_CLUSTER"); force = e ? atoi(e) : 0; }
     if (force >= 1 && force <= 3) cl = force;
     if (p.m_tiles < 2 || bn_tile < 64) cl = 1;
+    if (cl != 1) p.ksplit = 1;   // split-K is implemented for the single-CTA mode only
+    else if (p.ksplit > 1 && !p.fast_epi) p.ksplit = 1;
   }
   // tensor maps
   CUtensorMap am[4];
@@ -836,6 +912,11 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
     if (rc) return rc;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p.ksplit > 1) {   // the partial sums are red.added into a zeroed output
+    const size_t rows = static_cast<size_t>(d->W) * d->H * d->NB;
+    cudaError_t e = cudaMemset2DAsync(d->out_f32, static_cast<size_t>(d->ld_f32) * 4, 0, static_cast<size_t>(d->Ncols) * 4, rows, st);
+    if (e != cudaSuccess) return set_error(TNG_ECUDA, "cudaMemset2DAsync(split-K output): %s", cudaGetErrorString(e));
+  }
   switch (bn_tile) {
     case 32: return launch_gemm<32>(am, bm, p, st, cl);
     case 64: return launch_gemm<64>(am, bm, p, st, cl);

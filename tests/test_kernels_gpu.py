@@ -422,3 +422,40 @@ def test_gated_tanh_gelu_epilogue(cuda):
     ref = proj[:, :inner] * F.gelu(proj[:, inner:], approximate="tanh")
     torch.cuda.synchronize()
     assert rel_err(obs[:, :inner].float() + obs[:, inner:].float(), ref) < 5e-5
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,sc", [(16, 32, 2, 1280, 1280, 0), (5, 32, 2, 640, 320, 0), (16, 32, 2, 1280, 1280, 640)])
+def test_conv3x3_underfilled_split_k(cuda, NB, H, W, Cin, Cout, sc):
+    """Under-filled launches with a long reduction (the 32x2 level of the UNet) take the split-K path: two CTAs per
+    output tile red.add their fp32 partials into a zeroed output; bias / time vector / residual enter once; a fused
+    1x1 shortcut rides along as an extra k-group. The 5-image case has a ragged last M tile."""
+    g = torch.Generator(device="cpu").manual_seed(NB + Cin + sc)
+    x = torch.randn(NB, Cin, H, W, generator=g).to(cuda)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)).to(cuda)
+    b = torch.randn(Cout, generator=g).to(cuda)
+    temb = torch.randn(NB, Cout, generator=g).to(cuda)
+    xb = bf(nhwc_rows(x))
+    of = torch.full((NB * H * W, Cout), float("nan"), device=cuda)
+    if sc:
+        xs = torch.randn(NB, sc, H, W, generator=g).to(cuda)
+        ws = (torch.randn(Cout, sc, 1, 1, generator=g) / math.sqrt(sc)).to(cuda)
+        bs = torch.randn(Cout, generator=g).to(cuda)
+        pc = ops.PackedConv(w, b, split=False, device=cuda, sc_w=ws, sc_b=bs)
+        ops.run_conv(pc, xb, NB, H, W, sc_x=bf(nhwc_rows(xs)), rowvec=temb, out_f32=of)
+        ref = F.conv2d(bf(x).float(), bf(w).float(), b, padding=1) + temb[:, :, None, None]
+        ref = nhwc_rows(ref + F.conv2d(bf(xs).float(), bf(ws).float(), bs))
+    else:
+        res = torch.randn(NB * H * W, Cout, generator=g).to(cuda)
+        pc = ops.PackedConv(w, b, split=False, device=cuda)
+        ops.run_conv(pc, xb, NB, H, W, rowvec=temb, res=res, alpha=0.5, out_f32=of)
+        ref = F.conv2d(bf(x).float(), bf(w).float(), b, padding=1) + temb[:, :, None, None]
+        ref = (nhwc_rows(ref) + res) * 0.5
+    torch.cuda.synchronize()
+    assert rel_err(of, ref) < 2e-5
+    of2 = torch.full_like(of, float("nan"))
+    if sc:
+        ops.run_conv(pc, xb, NB, H, W, sc_x=bf(nhwc_rows(xs)), rowvec=temb, out_f32=of2)
+    else:
+        ops.run_conv(pc, xb, NB, H, W, rowvec=temb, res=res, alpha=0.5, out_f32=of2)
+    torch.cuda.synchronize()
+    assert torch.equal(of, of2)     # two partials per element: order-independent, run-to-run identical
