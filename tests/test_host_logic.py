@@ -1,5 +1,7 @@
 """CPU: host-side logic of the product (no GPU compute): scheduler grids / coefficient tables against the oracle,
 weight packing, state_dict shapes, k-group construction, and that GPU-only entry points refuse CPU tensors."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -173,3 +175,55 @@ def test_t5_config_recovered_from_state_dict():
     shapes = synth.t5_encoder_param_shapes(cfg)
     te = {k: torch.empty(s, device="meta") for k, s in shapes.items()}
     assert t5_config_from_state_dict(te) == cfg
+
+
+def test_cli_manifest_wav_and_paths(tmp_path):
+    """tango_b200.cli host pieces: inference_hf.py:30-66 argument names/defaults, :86-87 manifest parsing,
+    :91-93 output directory naming, :107 16 kHz PCM-16 wav files."""
+    import json
+    import wave
+    from tango_b200 import cli
+    a = cli.parse_args([])
+    assert (a.checkpoint, a.test_file, a.text_key, a.device) == ("declare-lab/tango", "data/test_audiocaps_subset.json",
+                                                                 "captions", "cuda:0")
+    assert (a.num_steps, a.guidance, a.batch_size) == (200, 3, 8)
+    man = tmp_path / "prompts.json"
+    man.write_text("\n".join(json.dumps({"captions": c, "id": i}) for i, c in enumerate(["a dog", "rain", "bells"])) + "\n\n")
+    assert cli.read_prompts(str(man), "captions") == ["a dog", "rain", "bells"]
+    assert cli.output_dir_for("outputs", "17", 200, 3.0) == "outputs/17_steps_200_guidance_3.0"
+    x = (np.sin(np.arange(1600) / 10.0) * 20000).astype(np.int16)
+    cli.write_wav(str(tmp_path / "o.wav"), x)
+    with wave.open(str(tmp_path / "o.wav")) as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 16000, 1600)
+        assert np.array_equal(np.frombuffer(w.readframes(1600), dtype="<i2"), x)
+    with pytest.raises(TypeError):
+        cli.write_wav(str(tmp_path / "f.wav"), x.astype(np.float32))
+
+
+def test_cli_main_flow_with_stub_model(tmp_path, monkeypatch):
+    """The whole CLI flow on the CPU with the model stubbed out: sharded indices, wav files, summary line."""
+    import json
+    from types import SimpleNamespace
+    from tango_b200 import cli
+    man = tmp_path / "p.json"
+    man.write_text("\n".join(json.dumps({"captions": f"prompt {i}"}) for i in range(5)))
+    calls = []
+
+    class Stub:
+        scheduler = SimpleNamespace(config={"num_train_timesteps": 1000})
+        model = SimpleNamespace(text_encoder=SimpleNamespace(synthetic=True))
+
+        def generate_for_batch(self, prompts, steps, guidance, batch_size, **kw):
+            calls.append((list(prompts), steps, guidance, batch_size, kw))
+            return [np.full(1600, i, dtype=np.int16) for i in range(len(prompts))]
+
+    monkeypatch.setattr(cli, "build_tango", lambda *a, **k: Stub())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    res = cli.main(["--test_file", str(man), "--num_steps", "7", "--guidance", "2.5", "--batch_size", "4",
+                    "--output_root", str(tmp_path / "o"), "--exp_id", "x", "--latent_h", "32"])
+    assert calls == [([f"prompt {i}" for i in range(5)], 7, 2.5, 4, {"latent_shape": (32, 16)})]
+    out = tmp_path / "o" / "x_steps_7_guidance_2.5"
+    assert res["output_dir"] == str(out) and sorted(os.listdir(out)) == [f"output_{j}.wav" for j in range(5)]
+    assert abs(res["audio_seconds"] - 0.5) < 1e-9 and res["text_encoder"] == "synthetic"
+    line = json.loads((tmp_path / "o" / "tango_checkpoint_summary.jsonl").read_text().strip())
+    assert line["Steps"] == 7 and line["Test Instances"] == 5 and line["scheduler_config"] == {"num_train_timesteps": 1000}

@@ -265,3 +265,24 @@ def test_prompts_through_tokenizer_t5_and_unet(cuda):
     b2 = t.model.inference(prompts, t.scheduler, 2, 3.0, 1, latent_shape=(32, 16), generator=g, prompt_embeds=pe1,
                            boolean_prompt_mask=pm1)
     assert rel(a, b2) < 1e-4
+
+
+def test_cli_generates_wavs_and_summary(cuda, tmp_path):
+    """python -m tango_b200.cli on the tiny synthetic model: one wav per prompt under its global index + a summary line."""
+    import json
+    import wave
+    from tango_b200 import cli
+    man = tmp_path / "prompts.json"
+    man.write_text("\n".join(json.dumps({"captions": c}) for c in ["a dog barking", "rain", "church bells ringing"]))
+    res = cli.main(["--checkpoint", "synthetic:tiny", "--test_file", str(man), "--num_steps", "2", "--batch_size", "2",
+                    "--device", str(cuda), "--output_root", str(tmp_path / "outputs"), "--exp_id", "t", "--latent_h", "32",
+                    "--seed", "0"])
+    out = tmp_path / "outputs" / "t_steps_2_guidance_3"          # the default guidance prints as `3`, as in the reference
+    assert res["output_dir"] == str(out) and res["Test Instances"] == 3
+    assert res["audio_seconds"] > 0 and res["audio_seconds_per_second"] > 0
+    for j in range(3):
+        with wave.open(str(out / f"output_{j}.wav")) as w:
+            # 32 latent frames -> 128 mel frames -> 160 samples each + the 32-sample ConvTranspose tail
+            assert w.getframerate() == 16000 and w.getnframes() == 128 * 160 + 32
+    line = (tmp_path / "outputs" / "tango_checkpoint_summary.jsonl").read_text().strip()
+    assert json.loads(line)["Steps"] == 2
