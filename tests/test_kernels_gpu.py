@@ -459,3 +459,4 @@ def test_conv3x3_underfilled_split_k(cuda, NB, H, W, Cin, Cout, sc):
         ops.run_conv(pc, xb, NB, H, W, rowvec=temb, res=res, alpha=0.5, out_f32=of2)
     torch.cuda.synchronize()
     assert torch.equal(of, of2)     # two partials per element: order-independent, run-to-run identical
+
