@@ -35,4 +35,6 @@ def test_attention_growing_scores_take_the_rescale_path(cuda, nsplit):
         ref = attn_ref(q.double(), k.double(), v.double(), heads, 0.125)
         torch.cuda.synchronize()
         rec = out[:, :Cc].float() + out[:, Cc:].float()
-        assert rel_err(rec.view(B, Lq, Cc).cpu(), ref.float()) < 1e-4
+        # hi/lo products carry ~2^-16 relative error per term; scores reach ~20 nats here, so allow 5e-4 (a wrong
+        # rescale would be off by O(1))
+        assert rel_err(rec.view(B, Lq, Cc).cpu(), ref.float()) < 5e-4
