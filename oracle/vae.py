@@ -66,3 +66,39 @@ def decode_first_stage(sd: SD, z: torch.Tensor, scale_factor: float, ch_mult=(1,
             h = _conv(sd, f"{d}.up.{lvl}.upsample.conv", h)
     h = _swish(_gn(sd, d + ".norm_out", h))
     return _conv(sd, d + ".conv_out", h)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Encoder side (SURVEY.md section 8(f).2 — the step *before* the hot path, used for training / audio-to-audio; restated
+# and pinned now so that the kernels of a later round have their checker ready).
+def downsample(sd: SD, p: str, x):
+    """modules.py:76-94 (Downsample, with_conv): zero-pad one column / row at the END of each axis, 3x3 stride-2 conv."""
+    x = F.pad(x, (0, 1, 0, 1), mode="constant", value=0)
+    return F.conv2d(x, sd[p + ".conv.weight"], sd[p + ".conv.bias"], stride=2, padding=0)
+
+
+def encoder_forward(sd: SD, x: torch.Tensor, ch_mult=(1, 2, 4), num_res_blocks=2) -> torch.Tensor:
+    """modules.py:519-543 (Encoder.forward) for the Tango VAE config (no attention inside the levels:
+    attn_resolutions = [], no time-stride-4 levels): mel (B, 1, T, 64) -> (B, 2 * z_channels, T/4, 16)."""
+    e = "encoder"
+    h = _conv(sd, e + ".conv_in", x)
+    for lvl in range(len(ch_mult)):
+        for blk in range(num_res_blocks):
+            h = resnet_block(sd, f"{e}.down.{lvl}.block.{blk}", h)
+        if lvl != len(ch_mult) - 1:
+            h = downsample(sd, f"{e}.down.{lvl}.downsample", h)
+    h = resnet_block(sd, e + ".mid.block_1", h)
+    h = attn_block(sd, e + ".mid.attn_1", h)
+    h = resnet_block(sd, e + ".mid.block_2", h)
+    h = _swish(_gn(sd, e + ".norm_out", h))
+    return _conv(sd, e + ".conv_out", h)
+
+
+def encode_first_stage(sd: SD, mel: torch.Tensor, ch_mult=(1, 2, 4), num_res_blocks=2):
+    """autoencoder.py:52-58,110-112 (encode / encode_first_stage) + distributions.py:24-41: returns (mean, std) of the
+    diagonal Gaussian posterior; `posterior.sample()` = mean + std * randn, `posterior.mode()` = mean;
+    the latent handed to the diffusion model is `scale_factor * sample` (models.py: get_first_stage_encoding)."""
+    moments = F.conv2d(encoder_forward(sd, mel, ch_mult, num_res_blocks), sd["quant_conv.weight"], sd["quant_conv.bias"])
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    return mean, torch.exp(0.5 * logvar)

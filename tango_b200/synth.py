@@ -197,6 +197,50 @@ def vae_decoder_param_shapes(vae_cfg: dict = VAE_CONFIG) -> Shapes:
     return s
 
 
+def vae_encoder_param_shapes(vae_cfg: dict = None) -> Shapes:
+    """encoder.* and quant_conv.* of the AudioLDM AutoencoderKL state_dict
+    (audioldm/variational_autoencoder/modules.py:419-517; autoencoder.py:28-29) — the "next" row 2 of the scope table."""
+    vae_cfg = vae_cfg or VAE_CONFIG
+    s: Shapes = OrderedDict()
+    dd = vae_cfg["ddconfig"]
+    ch, mult, nrb, zc = dd["ch"], dd["ch_mult"], dd["num_res_blocks"], dd["z_channels"]
+
+    def conv(p, o, i, k):
+        s[p + ".weight"] = (o, i, k, k)
+        s[p + ".bias"] = (o,)
+
+    def norm(p, c):
+        s[p + ".weight"] = (c,)
+        s[p + ".bias"] = (c,)
+
+    def res(p, i, o):
+        norm(p + ".norm1", i)
+        conv(p + ".conv1", o, i, 3)
+        norm(p + ".norm2", o)
+        conv(p + ".conv2", o, o, 3)
+        if i != o:
+            conv(p + ".nin_shortcut", o, i, 1)
+
+    conv("encoder.conv_in", ch, dd["in_channels"], 3)
+    bi = ch
+    for lvl in range(len(mult)):
+        bo = ch * mult[lvl]
+        for b in range(nrb):
+            res(f"encoder.down.{lvl}.block.{b}", bi, bo)
+            bi = bo
+        if lvl != len(mult) - 1:
+            conv(f"encoder.down.{lvl}.downsample.conv", bi, bi, 3)
+    res("encoder.mid.block_1", bi, bi)
+    norm("encoder.mid.attn_1.norm", bi)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(f"encoder.mid.attn_1.{n}", bi, bi, 1)
+    res("encoder.mid.block_2", bi, bi)
+    norm("encoder.norm_out", bi)
+    conv("encoder.conv_out", 2 * zc if dd.get("double_z", True) else zc, bi, 3)
+    conv("quant_conv", 2 * vae_cfg["embed_dim"], 2 * zc, 1)
+    return s
+
+
 TINY_T5_CONFIG = {"vocab_size": 96, "d_model": 128, "d_kv": 64, "num_heads": 2, "d_ff": 256, "num_layers": 2,
                   "relative_attention_num_buckets": 32, "relative_attention_max_distance": 128,
                   "layer_norm_epsilon": 1e-6, "feed_forward_proj": "gated-gelu"}

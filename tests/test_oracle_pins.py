@@ -162,3 +162,13 @@ def test_t5_bucket_known_answers():
     rel = torch.tensor([0, -1, -7, -8, -15, -16, -127, -128, -1000, 1, 7, 8, 127, 128, 1000])
     b = ot5.relative_position_bucket(rel, 32, 128).tolist()
     assert b == [0, 1, 7, 8, 9, 10, 15, 15, 15, 17, 23, 24, 31, 31, 31]
+
+
+def test_tiny_vae_encoder_golden():
+    """oracle/vae.py:encode_first_stage against the reference AutoencoderKL.encode_first_stage posterior
+    (tests/golden/tiny_vae_encoder.npz, oracle/make_golden_vae_encoder.py) — checker for the "next" row 2."""
+    gd = gold("tiny_vae_encoder.npz")
+    esd = synth.synth_state_dict(synth.vae_encoder_param_shapes(), seed=0)
+    mean, std = ovae.encode_first_stage(esd, torch.from_numpy(gd["mel"]))
+    assert mean.shape == (2, 8, 16, 16)
+    assert np.abs(mean.numpy() - gd["mean"]).max() < 1e-5 and np.abs(std.numpy() - gd["std"]).max() < 1e-5
