@@ -172,3 +172,23 @@ def test_tiny_vae_encoder_golden():
     mean, std = ovae.encode_first_stage(esd, torch.from_numpy(gd["mel"]))
     assert mean.shape == (2, 8, 16, 16)
     assert np.abs(mean.numpy() - gd["mean"]).max() < 1e-5 and np.abs(std.numpy() - gd["std"]).max() < 1e-5
+
+
+def test_tiny_stft_frontend_golden():
+    """oracle/stft.py (waveform conditioning, windowed-DFT magnitude, mel projection, log compression, padding) against
+    the reference's STFT / TacotronSTFT / torch_tools arithmetic (tests/golden/tiny_stft.npz, oracle/make_golden_stft.py)."""
+    from oracle import stft as ostft
+    gd = gold("tiny_stft.npz")
+    FL, HOP, WIN, NMEL, target = (int(v) for v in gd["cfg"])
+    basis = ostft.forward_basis(FL, WIN)
+    assert basis.shape == (2 * (FL // 2 + 1), 1, FL)
+    fb, lm, wav = ostft.wav_to_fbank([torch.from_numpy(gd["wave0"]), torch.from_numpy(gd["wave1"])], basis,
+                                     torch.from_numpy(gd["mel_basis"]), target_length=target, filter_length=FL,
+                                     hop_length=HOP)
+    assert fb.shape == (2, target, NMEL) and lm.shape == (2, target, FL // 2)
+    assert np.abs(wav.numpy() - gd["wav"]).max() < 1e-6
+    assert np.abs(fb.numpy() - gd["fbank"]).max() < 1e-5 and np.abs(lm.numpy() - gd["log_mag"]).max() < 1e-5
+    # DFT sanity: a pure tone at bin 8 puts its energy in magnitude bin 8
+    t = torch.arange(FL * 4, dtype=torch.float32)
+    mag = ostft.stft_magnitude(0.5 * torch.sin(2 * np.pi * 8 * t / FL)[None], basis, FL, HOP)
+    assert int(mag[0, :, 5].argmax()) == 8
