@@ -351,7 +351,7 @@ def run_ours(args):
     # (BASELINE.json's metric excludes text encoding). FLAN-T5 encoder of the UNet's width, seeded random weights,
     # `batch` prompts x `tokens` tokens (the "" prompt is cached by the pipeline and not re-encoded).
     text = None
-    if rank == 0 and not args.no_text_encoder:
+    if world == 1 and not args.no_text_encoder:          # like the CPU baseline: reported at N = 1 only
         text = text_encoder_leg(args, dev)
 
     # ---------------- CPU baseline (oracle port) on a bounded sample, N = 1 only
