@@ -1,0 +1,77 @@
+"""Fixtures for the diffusers fork's own known-answer block tests (TEST INFRASTRUCTURE ONLY; build container only).
+
+mustango/diffusers/tests/test_layers_utils.py builds each block with `torch.manual_seed(0)` default initialisation
+and compares an output slice with hard-coded constants. The constants live in tests/test_oracle_pins.py (cited there);
+this script reproduces the seeded inputs + module weights through the UNMODIFIED reference modules, checks that the
+reference still meets its constants on this torch build, and stores inputs + weights so the oracle's block functions can
+be checked against the same constants anywhere.
+
+    python -m oracle.make_golden_blocks
+"""
+import os
+
+import numpy as np
+import torch
+
+from oracle import refshim
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+EXPECTED = {   # test_layers_utils.py: ResnetBlock2D :226-240, Upsample2D with conv :131-141, Downsample2D pad 1 :200-210,
+               # Transformer2DModel with cross attention :394-418
+    "resnet": [-1.9010, -0.2974, -0.8245, -1.3533, 0.8742, -0.9645, -2.0584, 1.3387, -0.4746],
+    "upsample": [0.7145, 1.3773, 0.3492, 0.8448, 1.0839, -0.3341, 0.5956, 0.1250, -0.4841],
+    "downsample": [0.9267, 0.5878, 0.3337, 1.2321, -0.1191, -0.3984, -0.7532, -0.0715, -0.3913],
+    "transformer": [-0.2555, -0.8877, -2.4739, -2.2251, 1.2714, 0.0807, -0.4161, -1.6408, -0.0471],
+}
+
+
+def main():
+    torch.set_grad_enabled(False)
+    refshim.install()
+    from diffusers.models.resnet import Downsample2D, ResnetBlock2D, Upsample2D
+    from diffusers.models.transformer_2d import Transformer2DModel
+    out = {}
+
+    def check(name, y):
+        sl = y[0, -1, -3:, -3:].flatten()
+        d = float((sl - torch.tensor(EXPECTED[name])).abs().max())
+        print(f"{name}: reference module vs its own hard-coded slice: {d:.2e}")
+        assert d < 1e-3
+
+    torch.manual_seed(0)
+    x = torch.randn(1, 32, 64, 64)
+    temb = torch.randn(1, 128)
+    m = ResnetBlock2D(in_channels=32, temb_channels=128)
+    check("resnet", m(x, temb))
+    out.update({"resnet_x": x, "resnet_temb": temb, **{"resnet." + k: v for k, v in m.state_dict().items()}})
+
+    torch.manual_seed(0)
+    x = torch.randn(1, 32, 32, 32)
+    m = Upsample2D(channels=32, use_conv=True)
+    check("upsample", m(x))
+    out.update({"upsample_x": x, **{"upsample." + k: v for k, v in m.state_dict().items()}})
+
+    torch.manual_seed(0)
+    x = torch.randn(1, 32, 64, 64)
+    m = Downsample2D(channels=32, use_conv=True, padding=1)
+    check("downsample", m(x))
+    out.update({"downsample_x": x, **{"downsample." + k: v for k, v in m.state_dict().items()}})
+
+    torch.manual_seed(0)
+    x = torch.randn(1, 64, 64, 64)
+    m = Transformer2DModel(in_channels=64, num_attention_heads=2, attention_head_dim=32, dropout=0.0,
+                           cross_attention_dim=64)
+    ctx = torch.randn(1, 4, 64)
+    check("transformer", m(x, ctx).sample)
+    out.update({"transformer_x": x, "transformer_ctx": ctx, **{"transformer." + k: v for k, v in m.state_dict().items()}})
+
+    # the big input tensors are reproducible from the seed (torch CPU RNG): store only a checksum of each
+    for k in [k for k in out if k.endswith("_x")]:
+        out[k + "_sum"] = out.pop(k).double().sum().float()
+    np.savez_compressed(os.path.join(GOLD, "block_known_answers.npz"), **{k: v.numpy() for k, v in out.items()})
+    print("wrote", os.path.join(GOLD, "block_known_answers.npz"), f"({len(out)} arrays)")
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,16 @@ def resnet_block(sd: SD, p: str, x: torch.Tensor, temb: torch.Tensor, groups: in
     return (x + h) / 1.0
 
 
+def downsample2d(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
+    """D/models/resnet.py:199-208 (Downsample2D, use_conv=True, padding=1): 3x3 stride-2 conv."""
+    return _conv(sd, p + ".conv", x, stride=2, padding=1)
+
+
+def upsample2d(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
+    """D/models/resnet.py:126-161 (Upsample2D, use_conv=True): nearest x2 then 3x3 conv."""
+    return _conv(sd, p + ".conv", F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
 def attention(sd: SD, p: str, x: torch.Tensor, ctx: Optional[torch.Tensor], heads: int,
               bias: Optional[torch.Tensor]) -> torch.Tensor:
     """D/models/attention_processor.py:263-299 (AttnProcessor: baddbmm + softmax + bmm; the fp32 result equals
@@ -139,7 +149,7 @@ def unet_forward(sd: SD, cfg: dict, sample: torch.Tensor, timestep, encoder_hidd
                 h = transformer_2d(sd, f"down_blocks.{i}.attentions.{j}", h, encoder_hidden_states, heads[i], groups, bias)
             skips.append(h)
         if i != len(boc) - 1:
-            h = _conv(sd, f"down_blocks.{i}.downsamplers.0.conv", h, stride=2, padding=1)
+            h = downsample2d(sd, f"down_blocks.{i}.downsamplers.0", h)
             skips.append(h)
     if taps is not None:
         taps["down"] = h
@@ -158,8 +168,7 @@ def unet_forward(sd: SD, cfg: dict, sample: torch.Tensor, timestep, encoder_hidd
             if bt == "CrossAttnUpBlock2D":
                 h = transformer_2d(sd, f"up_blocks.{i}.attentions.{j}", h, encoder_hidden_states, rheads[i], groups, bias)
         if i != len(boc) - 1:
-            h = F.interpolate(h, scale_factor=2.0, mode="nearest")
-            h = _conv(sd, f"up_blocks.{i}.upsamplers.0.conv", h)
+            h = upsample2d(sd, f"up_blocks.{i}.upsamplers.0", h)
 
     h = F.silu(_gn(sd, "conv_norm_out", h, groups, eps))
     return _conv(sd, "conv_out", h)

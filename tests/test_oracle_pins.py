@@ -192,3 +192,45 @@ def test_tiny_stft_frontend_golden():
     t = torch.arange(FL * 4, dtype=torch.float32)
     mag = ostft.stft_magnitude(0.5 * torch.sin(2 * np.pi * 8 * t / FL)[None], basis, FL, HOP)
     assert int(mag[0, :, 5].argmax()) == 8
+
+
+# Known-answer slices hard-coded in the diffusers fork's own block tests (mustango/diffusers/tests/test_layers_utils.py):
+# ResnetBlock2D default :226-240, Upsample2D with conv :131-141, Downsample2D with conv / padding 1 :200-210,
+# Transformer2DModel with cross attention :394-418. Each test seeds torch with 0, draws the input, then builds the module
+# with default initialisation; oracle/make_golden_blocks.py stores those module weights (tests/golden/block_known_answers.npz).
+BLOCK_KNOWN = {
+    "resnet": [-1.9010, -0.2974, -0.8245, -1.3533, 0.8742, -0.9645, -2.0584, 1.3387, -0.4746],
+    "upsample": [0.7145, 1.3773, 0.3492, 0.8448, 1.0839, -0.3341, 0.5956, 0.1250, -0.4841],
+    "downsample": [0.9267, 0.5878, 0.3337, 1.2321, -0.1191, -0.3984, -0.7532, -0.0715, -0.3913],
+    "transformer": [-0.2555, -0.8877, -2.4739, -2.2251, 1.2714, 0.0807, -0.4161, -1.6408, -0.0471],
+}
+
+
+def _seeded_input(gd, name, shape):
+    torch.manual_seed(0)
+    x = torch.randn(*shape)
+    if abs(float(x.double().sum()) - float(gd[name + "_x_sum"])) > 1e-3:
+        pytest.skip("torch CPU RNG stream differs from the build that wrote the fixture")
+    return x
+
+
+@pytest.mark.parametrize("name", sorted(BLOCK_KNOWN))
+def test_oracle_blocks_meet_reference_known_answers(name):
+    gd = gold("block_known_answers.npz")
+    sd = {k[len(name) + 1:]: torch.from_numpy(gd[k]) for k in gd.files if k.startswith(name + ".")}
+    if name == "resnet":
+        x = _seeded_input(gd, name, (1, 32, 64, 64))
+        sd = {"r." + k: v for k, v in sd.items()}
+        y = ounet.resnet_block(sd, "r", x, torch.from_numpy(gd["resnet_temb"]), 32, 1e-6)   # ResnetBlock2D defaults
+    elif name == "upsample":
+        y = ounet.upsample2d({"u." + k: v for k, v in sd.items()}, "u", _seeded_input(gd, name, (1, 32, 32, 32)))
+    elif name == "downsample":
+        y = ounet.downsample2d({"d." + k: v for k, v in sd.items()}, "d", _seeded_input(gd, name, (1, 32, 64, 64)))
+    else:
+        # the test's block uses 1x1-conv projections (use_linear_projection=False): identical arithmetic to the linear
+        # form the oracle restates (Tango's config), with the conv kernels viewed as matrices
+        x = _seeded_input(gd, name, (1, 64, 64, 64))
+        sd = {"t." + k: (v[:, :, 0, 0] if k in ("proj_in.weight", "proj_out.weight") else v) for k, v in sd.items()}
+        y = ounet.transformer_2d(sd, "t", x, torch.from_numpy(gd["transformer_ctx"]), 2, 32, None)
+    got = y[0, -1, -3:, -3:].flatten()
+    assert torch.allclose(got, torch.tensor(BLOCK_KNOWN[name]), atol=1e-3), (name, got)
