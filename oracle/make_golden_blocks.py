@@ -69,6 +69,51 @@ def main():
     # the big input tensors are reproducible from the seed (torch CPU RNG): store only a checksum of each
     for k in [k for k in out if k.endswith("_x")]:
         out[k + "_sum"] = out.pop(k).double().sum().float()
+    # ---- mustango/diffusers/tests/test_unet_2d_blocks.py + test_unet_blocks_common.py:41-105 (UNetBlockTesterMixin):
+    # hidden_states / temb from torch.manual_seed(0), the skip tensor from torch.manual_seed(1), THEN the block is built
+    # with default initialisation from the global stream; slices compared at atol 5e-3.
+    from diffusers.models import unet_2d_blocks as B
+
+    def common(kind, with_res):
+        g = torch.manual_seed(0)
+        hs = torch.randn(4, 32, 32, 32, generator=g)
+        temb = torch.randn(4, 128, generator=g)
+        inp = {"hidden_states": hs, "temb": temb}
+        if with_res:
+            g1 = torch.manual_seed(1)
+            inp["res_hidden_states_tuple"] = (torch.randn(4, 32, 32, 32, generator=g1),)
+        init = {"in_channels": 32, "out_channels": 32, "temb_channels": 128}
+        if kind == "up":
+            init["prev_output_channel"] = 32
+        if kind == "mid":
+            init.pop("out_channels")
+        return init, inp
+
+    UNET_BLOCKS = {   # name: (class, kind, skip input, cross-attention, expected slice (test_unet_2d_blocks.py line))
+        "DownBlock2D": (B.DownBlock2D, "down", False, False,
+                        [-0.0232, -0.9869, 0.8054, -0.0637, -0.1688, -1.4264, 0.4470, -1.3394, 0.0904]),          # :23-30
+        "CrossAttnDownBlock2D": (B.CrossAttnDownBlock2D, "down", False, True,
+                                 [0.2440, -0.6953, -0.2140, -0.3874, 0.1966, 1.2077, 0.0441, -0.7718, 0.2800]),    # :50-62
+        "UNetMidBlock2DCrossAttn": (B.UNetMidBlock2DCrossAttn, "mid", False, True,
+                                    [0.1879, 2.2653, 0.5987, 1.1568, -0.8454, -1.6109, -0.8919, 0.8306, 1.6758]),  # :168-179
+        "UpBlock2D": (B.UpBlock2D, "up", True, False,
+                      [-0.2041, -0.4165, -0.3022, 0.0041, -0.6628, -0.7053, 0.1928, -0.0325, 0.0523]),            # :200-211
+        "CrossAttnUpBlock2D": (B.CrossAttnUpBlock2D, "up", True, True,
+                               [-0.2796, -0.4364, -0.1067, -0.2693, 0.1894, 0.3869, -0.3470, 0.4584, 0.5091]),    # :226-241
+    }
+    for name, (cls, kind, with_res, cross, exp) in UNET_BLOCKS.items():
+        init, inp = common(kind, with_res)
+        if cross:
+            init["cross_attention_dim"] = 32
+        blk = cls(**init).eval()
+        y = blk(**inp)
+        y = y[0] if isinstance(y, tuple) else y
+        d = float((y[0, -1, -3:, -3:].flatten() - torch.tensor(exp)).abs().max())
+        print(f"{name}: reference block vs its own hard-coded slice: {d:.2e}")
+        assert d < 5e-3
+        out.update({f"{name}." + k: v for k, v in blk.state_dict().items()})
+        out[f"{name}_x_sum"] = inp["hidden_states"].double().sum().float()
+
     np.savez_compressed(os.path.join(GOLD, "block_known_answers.npz"), **{k: v.numpy() for k, v in out.items()})
     print("wrote", os.path.join(GOLD, "block_known_answers.npz"), f"({len(out)} arrays)")
 
