@@ -227,3 +227,35 @@ def test_cli_main_flow_with_stub_model(tmp_path, monkeypatch):
     assert abs(res["audio_seconds"] - 0.5) < 1e-9 and res["text_encoder"] == "synthetic"
     line = json.loads((tmp_path / "o" / "tango_checkpoint_summary.jsonl").read_text().strip())
     assert line["Steps"] == 7 and line["Test Instances"] == 5 and line["scheduler_config"] == {"num_train_timesteps": 1000}
+
+
+def test_product_scheduler_tables_meet_reference_loop_constants():
+    """The product's host-side coefficient tables (what tng_sched_step consumes), driven through the fork's own
+    full-loop known answers: schedulers/test_scheduler_ddim.py:106-140 (172.0067 / 52.5302 / 149.8295 / 149.0784) and
+    test_scheduler_ddpm.py:71-131 (258.9606 / 202.0296; 1000 steps, seeded noise)."""
+    n = 4 * 3 * 8 * 8
+    x_init = (torch.arange(n).reshape(3, 8, 8, 4) / n).permute(3, 0, 1, 2)       # dummy_sample_deter
+    model = lambda s, t: s * t / (t + 1)                                            # dummy_model
+    base = dict(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", clip_sample=True)
+    for extra, es, em in ((dict(prediction_type="epsilon"), 172.0067, 0.223967),
+                          (dict(prediction_type="v_prediction"), 52.5302, 0.0684),
+                          (dict(set_alpha_to_one=True, beta_start=0.01), 149.8295, 0.1951),
+                          (dict(set_alpha_to_one=False, beta_start=0.01), 149.0784, 0.1941)):
+        d = S.DDIMScheduler(**dict(base, **extra))
+        d.set_timesteps(10)
+        tab = d.coefficient_table()
+        x = x_init.clone()
+        for i, t in enumerate(d.timesteps):
+            x = emulate_step(tab[i], model(x, t), x, None)
+        assert abs(x.abs().sum().item() - es) < 1e-2 and abs(x.abs().mean().item() - em) < 1e-3
+    for pred, es, em in (("epsilon", 258.9606, 0.3372), ("v_prediction", 202.0296, 0.2631)):
+        d = S.DDPMScheduler(**dict(base, prediction_type=pred))
+        d.set_timesteps(1000)
+        tab = d.coefficient_table()
+        x = x_init.clone()
+        g = torch.manual_seed(0)
+        for i, t in enumerate(d.timesteps):
+            res = model(x, t)
+            noise = torch.randn(res.shape, generator=g) if int(t) > 0 else None
+            x = emulate_step(tab[i], res, x, noise)
+        assert abs(x.abs().sum().item() - es) < 1e-2 and abs(x.abs().mean().item() - em) < 1e-3

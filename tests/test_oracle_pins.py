@@ -278,3 +278,27 @@ def test_oracle_unet_blocks_meet_reference_known_answers(name):
         h = ounet.upsample2d(sd, "upsamplers.0", h)
     got = h[0, -1, -3:, -3:].flatten()
     assert torch.allclose(got, torch.tensor(UNET_BLOCK_KNOWN[name]), atol=5e-3), (name, got)
+
+
+def test_ddim_variance_and_alpha_to_one_constants():
+    """schedulers/test_scheduler_ddim.py:94-104 (`_get_variance` constants) and :124-140 (10-step loops with and without
+    `set_alpha_to_one`, beta_start = 0.01): the remaining DDIM known answers of the fork's tests."""
+    s = osched.OracleDDIM(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear")
+
+    def variance(t, prev_t):       # scheduling_ddim.py:_get_variance
+        a_t = s.alphas_cumprod[t]
+        a_prev = s.alphas_cumprod[prev_t] if prev_t >= 0 else s.final_alpha_cumprod
+        return float(((1 - a_prev) / (1 - a_t)) * (1 - a_t / a_prev))
+
+    for (t, p), want in (((0, 0), 0.0), ((420, 400), 0.14771), ((980, 960), 0.32460), ((487, 486), 0.00979),
+                         ((999, 998), 0.02)):
+        assert abs(variance(t, p) - want) < 1e-5
+    for one, es, em in ((True, 149.8295, 0.1951), (False, 149.0784, 0.1941)):
+        s = osched.OracleDDIM(num_train_timesteps=1000, beta_start=0.01, beta_end=0.02, beta_schedule="linear",
+                              clip_sample=True, set_alpha_to_one=one)
+        s.set_timesteps(10)
+        x = _dummy_sample_deter()
+        for t in s.timesteps:
+            x = s.step(_dummy_model(x, t), t, x)
+        assert abs(x.abs().sum().item() - es) < 1e-2
+        assert abs(x.abs().mean().item() - em) < 1e-3
