@@ -112,11 +112,26 @@ def transformer_2d(sd: SD, p: str, x: torch.Tensor, ctx: torch.Tensor, heads: in
     return h + res
 
 
+def _mask_bias(m: Optional[torch.Tensor], dtype) -> Optional[torch.Tensor]:
+    """bool mask (True = keep) -> additive bias [B, 1, L] (unet_2d_condition.py:575-579); other dtypes pass as bias."""
+    if m is None:
+        return None
+    if m.dtype is torch.bool:
+        m = (1 - m.to(dtype)) * -10000.0
+    return m.unsqueeze(1)
+
+
 def unet_forward(sd: SD, cfg: dict, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor,
-                 encoder_attention_mask: Optional[torch.Tensor] = None, taps: Optional[dict] = None) -> torch.Tensor:
+                 encoder_attention_mask: Optional[torch.Tensor] = None, taps: Optional[dict] = None,
+                 extra_streams=()) -> torch.Tensor:
     """D/models/unet_2d_condition.py:520-707 for the block types Tango's configs use
     (CrossAttnDownBlock2D / DownBlock2D / UNetMidBlock2DCrossAttn / UpBlock2D / CrossAttnUpBlock2D,
-    D/models/unet_2d_blocks.py:1022-1074,1325-1349,577-598,2490-2513,2195-2248)."""
+    D/models/unet_2d_blocks.py:1022-1074,1325-1349,577-598,2490-2513,2195-2248).
+
+    `extra_streams` restates the Mustango variant (D/models/unet_2d_condition_music.py:536-757 with the *Music blocks of
+    unet_2d_blocks.py:603-760,1079-1270,2251-2440): a sequence of (features [B, L, D], mask or None) pairs — beats then
+    chords — each consumed by one more Transformer2DModel (`attentions2`, `attentions3`) right after the text one at
+    every attention position. Empty for Tango."""
     boc = cfg["block_out_channels"]
     groups = cfg.get("norm_num_groups", 32)
     eps = cfg.get("norm_eps", 1e-5)
@@ -124,12 +139,14 @@ def unet_forward(sd: SD, cfg: dict, sample: torch.Tensor, timestep, encoder_hidd
     heads = ahd if isinstance(ahd, (list, tuple)) else [ahd] * len(boc)
     lpb = cfg.get("layers_per_block", 2)
 
-    bias = None
-    if encoder_attention_mask is not None:
-        m = encoder_attention_mask
-        if m.dtype is torch.bool:
-            m = (1 - m.to(sample.dtype)) * -10000.0  # :575-579
-        bias = m.unsqueeze(1)
+    bias = _mask_bias(encoder_attention_mask, sample.dtype)
+    extras = [(f, _mask_bias(m, sample.dtype)) for f, m in extra_streams]
+
+    def attend(prefix: str, j: int, h: torch.Tensor, nheads: int) -> torch.Tensor:
+        h = transformer_2d(sd, f"{prefix}.attentions.{j}", h, encoder_hidden_states, nheads, groups, bias)
+        for n, (feat, fbias) in enumerate(extras):
+            h = transformer_2d(sd, f"{prefix}.attentions{n + 2}.{j}", h, feat, nheads, groups, fbias)
+        return h
 
     t = timestep
     if not torch.is_tensor(t):
@@ -145,8 +162,8 @@ def unet_forward(sd: SD, cfg: dict, sample: torch.Tensor, timestep, encoder_hidd
     for i, bt in enumerate(cfg["down_block_types"]):
         for j in range(lpb):
             h = resnet_block(sd, f"down_blocks.{i}.resnets.{j}", h, temb, groups, eps)
-            if bt == "CrossAttnDownBlock2D":
-                h = transformer_2d(sd, f"down_blocks.{i}.attentions.{j}", h, encoder_hidden_states, heads[i], groups, bias)
+            if bt in ("CrossAttnDownBlock2D", "CrossAttnDownBlock2DMusic"):
+                h = attend(f"down_blocks.{i}", j, h, heads[i])
             skips.append(h)
         if i != len(boc) - 1:
             h = downsample2d(sd, f"down_blocks.{i}.downsamplers.0", h)
@@ -155,7 +172,7 @@ def unet_forward(sd: SD, cfg: dict, sample: torch.Tensor, timestep, encoder_hidd
         taps["down"] = h
 
     h = resnet_block(sd, "mid_block.resnets.0", h, temb, groups, eps)
-    h = transformer_2d(sd, "mid_block.attentions.0", h, encoder_hidden_states, heads[-1], groups, bias)
+    h = attend("mid_block", 0, h, heads[-1])
     h = resnet_block(sd, "mid_block.resnets.1", h, temb, groups, eps)
     if taps is not None:
         taps["mid"] = h
@@ -165,8 +182,8 @@ def unet_forward(sd: SD, cfg: dict, sample: torch.Tensor, timestep, encoder_hidd
         for j in range(lpb + 1):
             h = torch.cat([h, skips.pop()], dim=1)
             h = resnet_block(sd, f"up_blocks.{i}.resnets.{j}", h, temb, groups, eps)
-            if bt == "CrossAttnUpBlock2D":
-                h = transformer_2d(sd, f"up_blocks.{i}.attentions.{j}", h, encoder_hidden_states, rheads[i], groups, bias)
+            if bt in ("CrossAttnUpBlock2D", "CrossAttnUpBlock2DMusic"):
+                h = attend(f"up_blocks.{i}", j, h, rheads[i])
         if i != len(boc) - 1:
             h = upsample2d(sd, f"up_blocks.{i}.upsamplers.0", h)
 

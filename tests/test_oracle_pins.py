@@ -302,3 +302,20 @@ def test_ddim_variance_and_alpha_to_one_constants():
             x = s.step(_dummy_model(x, t), t, x)
         assert abs(x.abs().sum().item() - es) < 1e-2
         assert abs(x.abs().mean().item() - em) < 1e-3
+
+
+def test_tiny_unet_music_golden():
+    """The Mustango UNet variant (beat + chord cross-attentions after the text one at every attention position;
+    unet_2d_condition_music.py) through the same oracle code path, against the fork's UNet2DConditionModelMusic output
+    (tests/golden/tiny_unet_music.npz, oracle/make_golden_music.py) — checker for the "next" row 4."""
+    gd = gold("tiny_unet_music.npz")
+    cfg = dict(synth.TINY_UNET_CONFIG,
+               down_block_types=["CrossAttnDownBlock2DMusic"] * 3 + ["DownBlock2D"],
+               mid_block_type="UNetMidBlock2DCrossAttnMusic",
+               up_block_types=["UpBlock2D"] + ["CrossAttnUpBlock2DMusic"] * 3)
+    sd = {k: synth.synth_tensor(k, eval(shp), 0) for k, shp in zip(gd["keys"].tolist(), gd["shapes"].tolist())}
+    assert len(sd) == 1518
+    tt = lambda n: torch.from_numpy(gd[n])
+    out = ounet.unet_forward(sd, cfg, tt("sample"), torch.tensor(int(gd["t"])), tt("ehs"), tt("mask"),
+                             extra_streams=((tt("beat"), tt("bmask")), (tt("chord"), tt("cmask"))))
+    assert np.abs(out.numpy() - gd["out"]).max() < 5e-5
