@@ -187,6 +187,12 @@ def require_cuda(*ts: Optional[torch.Tensor]) -> None:
             raise TangoB200Error("tango_b200 kernels need CUDA tensors (there is no CPU fallback)")
 
 
+def require_cuda_device(device) -> None:
+    """Models refuse to pack / run anywhere but on a CUDA device (there is no CPU fallback)."""
+    if torch.device(device).type != "cuda":
+        raise TangoB200Error("tango_b200 runs on CUDA only: call .to('cuda') (there is no CPU fallback)")
+
+
 # --------------------------------------------------------------------------------------------------- conv / gemm
 class View:
     """A bf16 channels-last activation view (img, h, w, c) with element strides."""

@@ -128,8 +128,7 @@ class _SchedulerBase:
              variance_noise: Optional[torch.Tensor] = None, return_dict: bool = True, **_unused):
         """x_t -> x_{t-1} for NCHW fp32 CUDA tensors (reference layout). Noise comes from the torch RNG exactly as
         in the reference (randn of model_output's shape when t > 0) unless `variance_noise` is given."""
-        if not model_output.is_cuda:
-            raise L.TangoB200Error("scheduler.step runs on the GPU only (no CPU fallback)")
+        L.require_cuda(model_output)   # no CPU fallback
         i = self._row(timestep)
         coef = self.coefficient_table(sample.device)[i]
         B, Cc, H, W = sample.shape

@@ -134,8 +134,7 @@ class T5EncoderModel:
             return
         if self._sd is None:
             raise L.TangoB200Error("T5EncoderModel has no weights: call load_state_dict first")
-        if self.device.type != "cuda":
-            raise L.TangoB200Error("tango_b200 runs on CUDA only: call .to('cuda') (there is no CPU fallback)")
+        L.require_cuda_device(self.device)
         L.load()
         sd, dev, sp, cfg = self._sd, self.device, self.split, self.cfg
         f32 = lambda k: sd[k].detach().float().contiguous().to(dev)

@@ -132,8 +132,7 @@ class UNet2DConditionModel:
             return
         if self._sd is None:
             raise L.TangoB200Error("UNet2DConditionModel has no weights: call load_state_dict first")
-        if self.device.type != "cuda":
-            raise L.TangoB200Error("tango_b200 runs on CUDA only: call .to('cuda') (there is no CPU fallback)")
+        L.require_cuda_device(self.device)
         L.load()
         sd, dev, sp = self._sd, self.device, self.split
         cfg = self.config

@@ -72,8 +72,7 @@ class AutoencoderKL:
             return
         if self._sd is None:
             raise L.TangoB200Error("AutoencoderKL has no weights: call load_state_dict first")
-        if self._device.type != "cuda":
-            raise L.TangoB200Error("tango_b200 runs on CUDA only: call .to('cuda') (there is no CPU fallback)")
+        L.require_cuda_device(self._device)
         L.load()
         sd, dev, sp = self._sd, self._device, self.split
         dd = self.ddconfig
@@ -250,8 +249,7 @@ class AutoencoderKL:
         """(B, 8, T/4, 16) latents -> (B, 1, T, 64) log-mel (autoencoder.py:116-124)."""
         if predict_cids:
             raise NotImplementedError("predict_cids is not on the Tango path")
-        if not z.is_cuda:
-            raise L.TangoB200Error("decode_first_stage runs on the GPU only (no CPU fallback)")
+        L.require_cuda(z)   # no CPU fallback
         B, Cc, H, W = z.shape
         rows = z.float().permute(0, 2, 3, 1).reshape(B * H * W, Cc).contiguous()
         mel = self.decode_rows(rows, B, H, W)
@@ -314,8 +312,7 @@ class AutoencoderKL:
 
     def decode_to_waveform(self, dec: torch.Tensor) -> np.ndarray:
         """(B, 1, T, 64) mel -> int16 numpy (B, L) (autoencoder.py:66-69; hifigan/utilities.py:76-86)."""
-        if not dec.is_cuda:
-            raise L.TangoB200Error("decode_to_waveform runs on the GPU only (no CPU fallback)")
+        L.require_cuda(dec)   # no CPU fallback
         B, _, T, nm = dec.shape
         rows = dec.float().reshape(B * T, nm).contiguous()  # squeeze(1).permute(0,2,1) in channels-last = same memory
         _, wi = self.vocoder_rows(rows, B, T)
