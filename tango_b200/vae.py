@@ -21,8 +21,31 @@ import torch
 
 from . import lib as L
 from .ops import PackedConv, run_conv, run_linear
-from .synth import HIFIGAN_CONFIG, VAE_CONFIG, vae_decoder_param_shapes
+from .synth import HIFIGAN_CONFIG, VAE_CONFIG, vae_decoder_param_shapes, vae_encoder_param_shapes
 from .unet import _Buffers
+
+
+class DiagonalGaussianDistribution:
+    """audioldm/variational_autoencoder/distributions.py:24-41 (mean | logvar channel halves, logvar clamped to
+    [-30, 20]); `sample()` draws from the torch RNG exactly as the reference does."""
+
+    def __init__(self, parameters: torch.Tensor, deterministic: bool = False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self, generator=None) -> torch.Tensor:
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype) \
+            if generator is not None else torch.randn(self.mean.shape).to(self.mean.device)
+        return self.mean + self.std * noise
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
 
 
 class AutoencoderKL:
@@ -35,6 +58,8 @@ class AutoencoderKL:
         self._device = torch.device("cpu")
         self._sd: Optional[Dict[str, torch.Tensor]] = None
         self._packed = False
+        self._esd: Optional[Dict[str, torch.Tensor]] = None     # encoder.* / quant_conv.* (optional)
+        self._epacked = False
         self.hifigan = dict(HIFIGAN_CONFIG)
 
     # ------------------------------------------------------------------------------------------ reference-style API
@@ -45,7 +70,7 @@ class AutoencoderKL:
         if device is not None and not isinstance(device, torch.dtype):
             device = torch.device(device)
             if device != self._device:
-                self._device, self._packed = device, False
+                self._device, self._packed, self._epacked = device, False, False
         return self
 
     def eval(self):
@@ -64,7 +89,15 @@ class AutoencoderKL:
                 raise RuntimeError(f"size mismatch for {k}: {tuple(sd[k].shape)} vs {tuple(shp)}")
         self._sd = {k: sd[k].detach() for k in want}
         self._packed = False
-        return SimpleNamespace(missing_keys=[], unexpected_keys=[k for k in sd if k not in want])
+        # encoder.* / quant_conv.* (pytorch_model_vae.bin carries them) enable encode_first_stage; they are optional
+        enc = vae_encoder_param_shapes(self._cfg())
+        self._esd, self._epacked = None, False
+        if all(k in sd for k in enc):
+            for k, shp in enc.items():
+                if tuple(sd[k].shape) != tuple(shp):
+                    raise RuntimeError(f"size mismatch for {k}: {tuple(sd[k].shape)} vs {tuple(shp)}")
+            self._esd = {k: sd[k].detach() for k in enc}
+        return SimpleNamespace(missing_keys=[], unexpected_keys=[k for k in sd if k not in want and k not in enc])
 
     # ------------------------------------------------------------------------------------------ packing
     def _pack(self):
@@ -168,9 +201,10 @@ class AutoencoderKL:
         run_conv(r.conv2, a2, NB, H, W, sc_x=raw, res=None if has_sc else x, out_f32=out)
         return out
 
-    def _attn(self, x, NB, H, W):
-        """modules.py:204-230: softmax(q k^T / sqrt(C)) v over the H*W positions of each image, one head."""
-        t = self.P.attn
+    def _attn(self, x, NB, H, W, t=None):
+        """modules.py:204-230: softmax(q k^T / sqrt(C)) v over the H*W positions of each image, one head.
+        `t`: packed attention weights (default: the decoder's mid block)."""
+        t = self.P.attn if t is None else t
         R, HW, s, sp, Cc = NB * H * W, H * W, self.s, self.split, t.C
         if HW % 64:
             raise L.TangoB200Error("VAE attention needs H*W to be a multiple of 64")
@@ -255,6 +289,115 @@ class AutoencoderKL:
         mel = self.decode_rows(rows, B, H, W)
         oc = mel.shape[1]
         return mel.view(B, 4 * H, 4 * W, oc).permute(0, 3, 1, 2).contiguous()
+
+    # ------------------------------------------------------------------------------------------ encoder
+    # SURVEY.md section 8(f).2 — the step in front of the diffusion model for training / audio-to-audio:
+    # audioldm/variational_autoencoder/modules.py:419-543 (Encoder), :76-94 (Downsample), autoencoder.py:52-58,110-112
+    # (encode / encode_first_stage), distributions.py:24-41. Same building blocks as the decoder; the stride-2
+    # Downsample pads one row / column at the END of each axis, which is PackedConv(stride=2, pad=0) on the TMA zero fill.
+    def _pack_encoder(self):
+        if self._epacked:
+            return
+        self._pack()
+        if self._esd is None:
+            raise L.TangoB200Error("AutoencoderKL was loaded without encoder.* / quant_conv.* weights")
+        sd, dev, sp, dd = self._esd, self._device, self.split, self.ddconfig
+
+        def f32(k):
+            return sd[k].float().contiguous().to(dev)
+
+        def conv(p, **kw):
+            return PackedConv(sd[p + ".weight"], sd.get(p + ".bias"), split=sp, device=dev, **kw)
+
+        def res(p):
+            r = SimpleNamespace()
+            r.n1w, r.n1b, r.n2w, r.n2b = f32(p + ".norm1.weight"), f32(p + ".norm1.bias"), f32(p + ".norm2.weight"), f32(p + ".norm2.bias")
+            r.conv1 = conv(p + ".conv1")
+            if (p + ".nin_shortcut.weight") in sd:
+                r.conv2 = PackedConv(sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], split=sp, device=dev,
+                                     sc_w=sd[p + ".nin_shortcut.weight"], sc_b=sd[p + ".nin_shortcut.bias"])
+            else:
+                r.conv2 = conv(p + ".conv2")
+            r.cin, r.cout = r.conv1.cin, r.conv1.cout
+            return r
+
+        E = SimpleNamespace()
+        w_in = sd["encoder.conv_in.weight"].float()
+        E.cin_pad = 8                                   # activation views need a multiple of 8 channels: zero-pad 1 -> 8
+        E.conv_in = PackedConv(torch.nn.functional.pad(w_in, (0, 0, 0, 0, 0, E.cin_pad - w_in.shape[1])),
+                               sd["encoder.conv_in.bias"], split=sp, device=dev)
+        E.down = []
+        nres = len(dd["ch_mult"])
+        for lvl in range(nres):
+            blk = SimpleNamespace(res=[res(f"encoder.down.{lvl}.block.{b}") for b in range(dd["num_res_blocks"])], down=None)
+            if lvl != nres - 1:
+                blk.down = conv(f"encoder.down.{lvl}.downsample.conv", stride=2, pad=0)
+            E.down.append(blk)
+        E.mid1, E.mid2 = res("encoder.mid.block_1"), res("encoder.mid.block_2")
+        a = "encoder.mid.attn_1"
+        E.attn = SimpleNamespace(nw=f32(a + ".norm.weight"), nb=f32(a + ".norm.bias"))
+        Cc = sd[a + ".q.weight"].shape[0]
+        wq = torch.cat([sd[a + ".q.weight"], sd[a + ".k.weight"], sd[a + ".v.weight"]], 0).reshape(3 * Cc, Cc)
+        bq = torch.cat([sd[a + ".q.bias"], sd[a + ".k.bias"], sd[a + ".v.bias"]], 0)
+        E.attn.qkv = PackedConv(wq, bq, split=sp, device=dev)
+        E.attn.proj = PackedConv(sd[a + ".proj_out.weight"].reshape(Cc, Cc), sd[a + ".proj_out.bias"], split=sp, device=dev)
+        E.attn.C = Cc
+        E.no_w, E.no_b = f32("encoder.norm_out.weight"), f32("encoder.norm_out.bias")
+        E.conv_out = conv("encoder.conv_out")
+        E.q_w = sd["quant_conv.weight"].float().reshape(sd["quant_conv.weight"].shape[0], -1).contiguous().to(dev)
+        E.q_b = f32("quant_conv.bias")
+        self.E = E
+        self._epacked = True
+
+    def encode_rows(self, mel_rows: torch.Tensor, NB: int, H: int, W: int) -> torch.Tensor:
+        """mel_rows fp32 [NB*H*W, 1] (channels-last log-mel, H = frames, W = 64 bins) -> moments fp32
+        [NB*(H/4)*(W/4), 2*embed_dim] (mean | logvar channels of the posterior)."""
+        self._pack_encoder()
+        E, s, sp = self.E, self.s, self.split
+        R = NB * H * W
+        x8 = torch.zeros(R, E.cin_pad, device=mel_rows.device, dtype=torch.float32)
+        x8[:, :mel_rows.shape[1]] = mel_rows
+        xb = self._buf("a", (R, E.cin_pad * s), torch.bfloat16)
+        L.cast_act(x8, NB, H, W, xb, split_off=E.cin_pad if sp else 0)
+        h = self._buf("econv_in", (R, E.conv_in.cout), torch.float32)
+        run_conv(E.conv_in, xb, NB, H, W, out_f32=h)
+        ch, cw = H, W
+        for li, blk in enumerate(E.down):
+            for bi, r in enumerate(blk.res):
+                h = self._resnet(f"edown{li}_{bi}", r, h, NB, ch, cw)
+            if blk.down is not None:
+                Cc = blk.down.cin
+                xb = self._buf("a", (NB * ch * cw, Cc * s), torch.bfloat16)
+                L.cast_act(h, NB, ch, cw, xb, split_off=Cc if sp else 0)
+                hd = self._buf(f"edown{li}_ds", (NB * (ch // 2) * (cw // 2), blk.down.cout), torch.float32)
+                run_conv(blk.down, xb, NB, ch, cw, out_f32=hd)
+                ch, cw = ch // 2, cw // 2
+                h = hd
+        h = self._resnet("emid1", E.mid1, h, NB, ch, cw)
+        h = self._attn(h, NB, ch, cw, E.attn)
+        h = self._resnet("emid2", E.mid2, h, NB, ch, cw)
+        Cc = h.shape[1]
+        a = self._buf("a", (NB * ch * cw, Cc * s), torch.bfloat16)
+        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
+        L.groupnorm(h, None, NB, ch * cw, 32, stats, E.no_w, E.no_b, 1e-6, L.ACT_SILU, a, split_off=Cc if sp else 0)
+        mom = self._buf("emom", (NB * ch * cw, E.conv_out.cout), torch.float32)
+        run_conv(E.conv_out, a, NB, ch, cw, out_f32=mom)
+        out = self._buf("emoments", (NB * ch * cw, E.q_w.shape[0]), torch.float32)
+        L.linear_f32(mom, E.q_w, E.q_b, out)
+        return out
+
+    def encode(self, x: torch.Tensor) -> "DiagonalGaussianDistribution":
+        """(B, 1, T, 64) log-mel -> posterior over (B, embed_dim, T/4, 16) latents (autoencoder.py:52-58)."""
+        L.require_cuda(x)   # no CPU fallback
+        B, Cc, T, Fq = x.shape
+        if Cc != 1 or T % 16 or Fq % 4:
+            raise L.TangoB200Error("encode expects (B, 1, T, F) with T a multiple of 16 and F of 4")
+        rows = x.float().permute(0, 2, 3, 1).reshape(B * T * Fq, 1).contiguous()
+        mom = self.encode_rows(rows, B, T, Fq)
+        return DiagonalGaussianDistribution(mom.view(B, T // 4, Fq // 4, -1).permute(0, 3, 1, 2).contiguous())
+
+    def encode_first_stage(self, x: torch.Tensor) -> "DiagonalGaussianDistribution":
+        return self.encode(x)
 
     # ------------------------------------------------------------------------------------------ vocoder
     def vocoder_rows(self, mel_rows: torch.Tensor, B: int, T: int):

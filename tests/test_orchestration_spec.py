@@ -112,3 +112,28 @@ def test_scheduler_step_orchestration_bit_exact():
         for t in si.timesteps.tolist():
             x = si.step(torch.sin(x * 3.0 + float(t) / 1000), t, x).prev_sample
         assert np.array_equal(x.numpy(), gd[f"ddim_loop_{pred}"])
+
+
+@pytest.mark.parametrize("precision,tol", [("split", 1e-4), ("bf16", 3e-2)])
+def test_vae_encoder_orchestration_vs_reference_golden(precision, tol):
+    """encode_first_stage (the "next" row 2): posterior mean / std against the reference AutoencoderKL
+    (tests/golden/tiny_vae_encoder.npz)."""
+    from tango_b200.vae import AutoencoderKL
+    gd = np.load(os.path.join(GOLD, "tiny_vae_encoder.npz"))
+    vae = AutoencoderKL(**synth.VAE_CONFIG, precision=precision).to(CPU)
+    sd = synth.synth_state_dict(synth.vae_decoder_param_shapes(), seed=0)
+    sd.update(synth.synth_state_dict(synth.vae_encoder_param_shapes(), seed=0))
+    vae.load_state_dict(sd)
+    post = vae.encode_first_stage(torch.from_numpy(gd["mel"]))
+    assert post.mean.shape == (2, 8, 16, 16)
+    assert rel(post.mean, gd["mean"]) < tol and rel(post.std, gd["std"]) < tol
+    assert torch.equal(post.mode(), post.mean)
+    torch.manual_seed(3)
+    z = post.sample()
+    torch.manual_seed(3)
+    assert torch.equal(z, post.mean + post.std * torch.randn(post.mean.shape))
+    # without encoder weights the decoder still loads and encode refuses loudly
+    dec_only = AutoencoderKL(**synth.VAE_CONFIG, precision=precision).to(CPU)
+    dec_only.load_state_dict(synth.synth_state_dict(synth.vae_decoder_param_shapes(), seed=0))
+    with pytest.raises(L.TangoB200Error):
+        dec_only.encode_first_stage(torch.from_numpy(gd["mel"]))
