@@ -25,9 +25,17 @@ TINY_UNET_CONFIG = {
     "use_linear_projection": True, "upcast_attention": True,
 }
 
+_MUSIC_BLOCKS = dict(
+    down_block_types=["CrossAttnDownBlock2DMusic", "CrossAttnDownBlock2DMusic", "CrossAttnDownBlock2DMusic", "DownBlock2D"],
+    mid_block_type="UNetMidBlock2DCrossAttnMusic",
+    up_block_types=["UpBlock2D", "CrossAttnUpBlock2DMusic", "CrossAttnUpBlock2DMusic", "CrossAttnUpBlock2DMusic"])
+# Mustango variant (mustango/configs/music_diffusion_model_config.json): beat + chord cross-attentions at every position
+TINY_MUSIC_UNET_CONFIG = dict(TINY_UNET_CONFIG, **_MUSIC_BLOCKS)
+
 BASE_UNET_CONFIG = dict(TINY_UNET_CONFIG, attention_head_dim=[5, 10, 20, 20], block_out_channels=[320, 640, 1280, 1280],
                         cross_attention_dim=1024)
 XL_UNET_CONFIG = dict(BASE_UNET_CONFIG, cross_attention_dim=2048)
+MUSIC_UNET_CONFIG = dict(BASE_UNET_CONFIG, **_MUSIC_BLOCKS)
 
 VAE_CONFIG = {"image_key": "fbank", "subband": 1, "embed_dim": 8, "time_shuffle": 1,
               "ddconfig": {"double_z": True, "z_channels": 8, "resolution": 256, "downsample_time": False,
@@ -103,9 +111,11 @@ def unet_param_shapes(cfg: dict) -> Shapes:
     for i, bt in enumerate(cfg["down_block_types"]):
         in_ch, out_ch = out_ch, boc[i]
         # diffusers registers attentions before resnets inside each block
-        if bt == "CrossAttnDownBlock2D":
-            for j in range(lpb):
-                transformer(f"down_blocks.{i}.attentions.{j}", out_ch)
+        if bt in ("CrossAttnDownBlock2D", "CrossAttnDownBlock2DMusic"):
+            # the Mustango blocks (unet_2d_blocks.py:1079-1270) add attentions2 (beats) and attentions3 (chords)
+            for name in ("attentions", "attentions2", "attentions3")[:3 if bt.endswith("Music") else 1]:
+                for j in range(lpb):
+                    transformer(f"down_blocks.{i}.{name}.{j}", out_ch)
         for j in range(lpb):
             resnet(f"down_blocks.{i}.resnets.{j}", in_ch if j == 0 else out_ch, out_ch)
         if i != len(boc) - 1:
@@ -118,9 +128,10 @@ def unet_param_shapes(cfg: dict) -> Shapes:
     for i, bt in enumerate(cfg["up_block_types"]):
         prev_out, out_ch = out_ch, rboc[i]
         in_ch = rboc[min(i + 1, len(boc) - 1)]
-        if bt == "CrossAttnUpBlock2D":
-            for j in range(lpb + 1):
-                transformer(f"up_blocks.{i}.attentions.{j}", out_ch)
+        if bt in ("CrossAttnUpBlock2D", "CrossAttnUpBlock2DMusic"):
+            for name in ("attentions", "attentions2", "attentions3")[:3 if bt.endswith("Music") else 1]:
+                for j in range(lpb + 1):
+                    transformer(f"up_blocks.{i}.{name}.{j}", out_ch)
         for j in range(lpb + 1):
             skip = in_ch if j == lpb else out_ch
             rin = prev_out if j == 0 else out_ch
@@ -130,6 +141,9 @@ def unet_param_shapes(cfg: dict) -> Shapes:
     s = main
     s.update(up)
     transformer("mid_block.attentions.0", boc[-1])
+    if cfg.get("mid_block_type", "UNetMidBlock2DCrossAttn") == "UNetMidBlock2DCrossAttnMusic":
+        transformer("mid_block.attentions2.0", boc[-1])
+        transformer("mid_block.attentions3.0", boc[-1])
     resnet("mid_block.resnets.0", boc[-1], boc[-1])
     resnet("mid_block.resnets.1", boc[-1], boc[-1])
     norm("conv_norm_out", boc[0])

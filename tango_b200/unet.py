@@ -57,8 +57,11 @@ class _Buffers:
 class UNet2DConditionModel:
     """See module docstring. `precision`: "bf16" (perf) or "split" (parity)."""
 
-    SUPPORTED_DOWN = ("CrossAttnDownBlock2D", "DownBlock2D")
-    SUPPORTED_UP = ("CrossAttnUpBlock2D", "UpBlock2D")
+    SUPPORTED_DOWN = ("CrossAttnDownBlock2D", "DownBlock2D", "CrossAttnDownBlock2DMusic")
+    SUPPORTED_UP = ("CrossAttnUpBlock2D", "UpBlock2D", "CrossAttnUpBlock2DMusic")
+    # The *Music types are the Mustango variant (SURVEY.md section 8(f).4; D/models/unet_2d_condition_music.py:536-757,
+    # unet_2d_blocks.py:603-760,1079-1270,2251-2440): every attention position runs two more Transformer2DModels
+    # (`attentions2` on beat features, `attentions3` on chord features) right after the text one.
 
     def __init__(self, config: dict, precision: str = "bf16"):
         cfg = dict(config)
@@ -190,21 +193,27 @@ class UNet2DConditionModel:
             blk = SimpleNamespace(resnets=[], attns=[], down=None)
             for j in range(lpb):
                 blk.resnets.append(resnet(f"down_blocks.{i}.resnets.{j}"))
-                if bt == "CrossAttnDownBlock2D":
+                if bt in ("CrossAttnDownBlock2D", "CrossAttnDownBlock2DMusic"):
                     blk.attns.append(transformer(f"down_blocks.{i}.attentions.{j}", heads[i]))
+                    blk.attns[-1].extra = [transformer(f"down_blocks.{i}.attentions{n}.{j}", heads[i])
+                                           for n in ((2, 3) if bt.endswith("Music") else ())]
             if i != len(boc) - 1:
                 blk.down = conv(f"down_blocks.{i}.downsamplers.0.conv", stride=2)
             P["down"].append(blk)
         P["mid"] = SimpleNamespace(r0=resnet("mid_block.resnets.0"), attn=transformer("mid_block.attentions.0", heads[-1]),
                                    r1=resnet("mid_block.resnets.1"))
+        mid_music = cfg.get("mid_block_type", "UNetMidBlock2DCrossAttn") == "UNetMidBlock2DCrossAttnMusic"
+        P["mid"].attn.extra = [transformer(f"mid_block.attentions{n}.0", heads[-1]) for n in ((2, 3) if mid_music else ())]
         rheads = list(reversed(heads))
         P["up"] = []
         for i, bt in enumerate(cfg["up_block_types"]):
             blk = SimpleNamespace(resnets=[], attns=[], up=None)
             for j in range(lpb + 1):
                 blk.resnets.append(resnet(f"up_blocks.{i}.resnets.{j}"))
-                if bt == "CrossAttnUpBlock2D":
+                if bt in ("CrossAttnUpBlock2D", "CrossAttnUpBlock2DMusic"):
                     blk.attns.append(transformer(f"up_blocks.{i}.attentions.{j}", rheads[i]))
+                    blk.attns[-1].extra = [transformer(f"up_blocks.{i}.attentions{n}.{j}", rheads[i])
+                                           for n in ((2, 3) if bt.endswith("Music") else ())]
             if i != len(boc) - 1:
                 blk.up = conv(f"up_blocks.{i}.upsamplers.0.conv")
             P["up"].append(blk)
@@ -222,6 +231,7 @@ class UNet2DConditionModel:
         P["temb_w"] = torch.cat([r.temb_w for r in res_all], 0).contiguous().to(dev)
         P["temb_b"] = torch.cat([r.temb_b for r in res_all], 0).contiguous().to(dev)
         P["transformers"] = [t for b in P["down"] for t in b.attns] + [P["mid"].attn] + [t for b in P["up"] for t in b.attns]
+        P["n_extra"] = max((len(t.extra) for t in P["transformers"]), default=0)
         self.P = P
         self._bufs = _Buffers(dev)
         self._packed = True
@@ -248,10 +258,14 @@ class UNet2DConditionModel:
         L.linear_f32(e2, P["temb_w"], P["temb_b"], out, pre_act=L.ACT_SILU)
         return out
 
-    def set_conditioning(self, encoder_hidden_states: torch.Tensor, encoder_attention_mask: Optional[torch.Tensor]):
+    def set_conditioning(self, encoder_hidden_states: torch.Tensor, encoder_attention_mask: Optional[torch.Tensor],
+                         extra_streams=()):
         """Project the (frozen, step-invariant) text states to K/V for all 16 cross-attention layers once
-        (attention_processor.py:279-284) and turn the mask into the additive bias of unet_2d_condition.py:575-579."""
+        (attention_processor.py:279-284) and turn the mask into the additive bias of unet_2d_condition.py:575-579.
+        `extra_streams`: ((features [Bu, L, D], mask or None), ...) for the Mustango blocks — beats, then chords."""
         self._pack()
+        if len(extra_streams) != self.P["n_extra"]:
+            raise L.TangoB200Error(f"this UNet needs {self.P['n_extra']} extra conditioning streams, got {len(extra_streams)}")
         ehs = encoder_hidden_states.to(self.device, torch.float32, non_blocking=True).contiguous()
         Bu, Lk, D = ehs.shape
         s = self.s
@@ -271,7 +285,26 @@ class UNet2DConditionModel:
                 bias.copy_((1 - m.to(torch.float32)) * -10000.0)
             else:
                 bias.copy_(m.to(torch.float32))
-        self._cond = SimpleNamespace(kvs=kvs, bias=bias, Bu=Bu, Lk=Lk)
+        extra = []
+        for n, (feat, fmask) in enumerate(extra_streams):
+            f = feat.to(self.device, torch.float32, non_blocking=True).contiguous()
+            if f.shape[0] != Bu or f.shape[2] != D:
+                raise L.TangoB200Error("extra conditioning streams must share the batch and feature width of the text states")
+            Ln = f.shape[1]
+            fb = self._buf(f"cond_x{n}", (Bu * Ln, D * s), torch.bfloat16)
+            L.cast_act(f.view(Bu * Ln, D), 1, 1, Bu * Ln, fb, split_off=D if self.split else 0)
+            xk = []
+            for i, t in enumerate(self.P["transformers"]):
+                kvn = self._buf(f"cond_x{n}kv{i}", (Bu * Ln, 2 * t.C * s), torch.bfloat16)
+                run_linear(t.extra[n].kv2, fb, out_bf16=kvn)
+                xk.append(kvn)
+            xb = None
+            if fmask is not None:
+                m = fmask.to(self.device, non_blocking=True)
+                xb = self._buf(f"cond_x{n}bias", (Bu, Ln), torch.float32)
+                xb.copy_((1 - m.to(torch.float32)) * -10000.0 if m.dtype is torch.bool else m.to(torch.float32))
+            extra.append(SimpleNamespace(kvs=xk, bias=xb, Lk=Ln))
+        self._cond = SimpleNamespace(kvs=kvs, bias=bias, Bu=Bu, Lk=Lk, extra=extra)
 
     def _resnet(self, name, r, x0, x1, NB, H, W, temb, temb_ld):
         R, HW, s, sp = NB * H * W, H * W, self.s, self.split
@@ -382,18 +415,28 @@ class UNet2DConditionModel:
         skips = [h]
         ti = 0
         ch, cw = H, W
+
+        def extras(name, t, hh, idx):
+            # Mustango: beat / chord transformers right after the text one (none for Tango)
+            for n, tx in enumerate(t.extra):
+                e = c.extra[n]
+                hh = self._transformer(f"{name}x{n}", tx, hh, NB, ch, cw, e.kvs[idx], e.bias, e.Lk)
+            return hh
+
         for i, blk in enumerate(P["down"]):
             for j, r in enumerate(blk.resnets):
                 first = shared and i == 0 and j == 0
                 if first:
                     hp = self._resnet("d0r0", r, h[:NBp * H * W], None, NBp, ch, cw, temb, temb_ld)
                     h = self._transformer("d0t0", blk.attns[0], hp, NB, ch, cw, c.kvs[ti], c.bias, c.Lk, shared_half=True)
+                    h = extras("d0t0", blk.attns[0], h, ti)
                     ti += 1
                     skips.append(h)
                     continue
                 h = self._resnet(f"d{i}r{j}", r, h, None, NB, ch, cw, temb, temb_ld)
                 if blk.attns:
                     h = self._transformer(f"d{i}t{j}", blk.attns[j], h, NB, ch, cw, c.kvs[ti], c.bias, c.Lk)
+                    h = extras(f"d{i}t{j}", blk.attns[j], h, ti)
                     ti += 1
                 skips.append(h)
             if blk.down is not None:
@@ -408,6 +451,7 @@ class UNet2DConditionModel:
         m = P["mid"]
         h = self._resnet("m0", m.r0, h, None, NB, ch, cw, temb, temb_ld)
         h = self._transformer("mt", m.attn, h, NB, ch, cw, c.kvs[ti], c.bias, c.Lk)
+        h = extras("mt", m.attn, h, ti)
         ti += 1
         h = self._resnet("m1", m.r1, h, None, NB, ch, cw, temb, temb_ld)
         for i, blk in enumerate(P["up"]):
@@ -416,6 +460,7 @@ class UNet2DConditionModel:
                 h = self._resnet(f"u{i}r{j}", r, h, skip, NB, ch, cw, temb, temb_ld)
                 if blk.attns:
                     h = self._transformer(f"u{i}t{j}", blk.attns[j], h, NB, ch, cw, c.kvs[ti], c.bias, c.Lk)
+                    h = extras(f"u{i}t{j}", blk.attns[j], h, ti)
                     ti += 1
             if blk.up is not None:
                 Cc = blk.up.cin
@@ -447,8 +492,12 @@ class UNet2DConditionModel:
     def forward(self, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor, class_labels=None,
                 timestep_cond=None, attention_mask=None, cross_attention_kwargs=None,
                 down_block_additional_residuals=None, mid_block_additional_residual=None,
-                encoder_attention_mask: Optional[torch.Tensor] = None, return_dict: bool = True):
-        """diffusers-compatible call: NCHW fp32 in, NCHW fp32 `.sample` out (unet_2d_condition.py:520-533)."""
+                encoder_attention_mask: Optional[torch.Tensor] = None, return_dict: bool = True,
+                beat_features: Optional[torch.Tensor] = None, chord_features: Optional[torch.Tensor] = None,
+                beat_attention_mask: Optional[torch.Tensor] = None, chord_attention_mask: Optional[torch.Tensor] = None):
+        """diffusers-compatible call: NCHW fp32 in, NCHW fp32 `.sample` out (unet_2d_condition.py:520-533). The
+        beat / chord arguments are those of the Mustango variant (unet_2d_condition_music.py:536-552) and are required
+        exactly when the config uses the *Music block types."""
         if attention_mask is not None or class_labels is not None or down_block_additional_residuals is not None:
             raise NotImplementedError("attention_mask / class_labels / controlnet residuals are not on the Tango path")
         self._pack()
@@ -459,7 +508,12 @@ class UNet2DConditionModel:
         ts = ts.reshape(-1).to(torch.float32)
         ts = ts.expand(B) if ts.numel() == 1 else ts
         temb = self.time_embedding_table(ts)
-        self.set_conditioning(encoder_hidden_states, encoder_attention_mask)
+        streams = ()
+        if beat_features is not None or chord_features is not None:
+            if beat_features is None or chord_features is None:
+                raise ValueError("beat_features and chord_features must be given together")
+            streams = ((beat_features, beat_attention_mask), (chord_features, chord_attention_mask))
+        self.set_conditioning(encoder_hidden_states, encoder_attention_mask, extra_streams=streams)
         out = self.forward_rows(self.input_rows(sample), B, H, W, temb, temb.shape[1])
         y = out.view(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
         if not return_dict:

@@ -137,3 +137,24 @@ def test_vae_encoder_orchestration_vs_reference_golden(precision, tol):
     dec_only.load_state_dict(synth.synth_state_dict(synth.vae_decoder_param_shapes(), seed=0))
     with pytest.raises(L.TangoB200Error):
         dec_only.encode_first_stage(torch.from_numpy(gd["mel"]))
+
+
+@pytest.mark.parametrize("precision,tol", [("split", 1e-4), ("bf16", 3e-2)])
+def test_mustango_unet_orchestration_vs_reference_golden(precision, tol):
+    """The Mustango UNet variant (beat + chord cross-attention streams; the "next" row 4) against the fork's
+    UNet2DConditionModelMusic output (tests/golden/tiny_unet_music.npz)."""
+    gd = np.load(os.path.join(GOLD, "tiny_unet_music.npz"))
+    cfg = synth.TINY_MUSIC_UNET_CONFIG
+    u = UNet2DConditionModel.from_config(cfg, precision=precision).to(CPU)
+    u.load_state_dict(synth.synth_state_dict(synth.unet_param_shapes(cfg), seed=0))
+    tt = lambda n: torch.from_numpy(gd[n])
+    out = u(tt("sample"), torch.tensor(int(gd["t"])), tt("ehs"), encoder_attention_mask=tt("mask"),
+            beat_features=tt("beat"), chord_features=tt("chord"), beat_attention_mask=tt("bmask"),
+            chord_attention_mask=tt("cmask")).sample
+    assert rel(out, gd["out"]) < tol
+    with pytest.raises(L.TangoB200Error):          # the Music blocks need their two extra streams
+        u(tt("sample"), 3, tt("ehs"))
+    plain = UNet2DConditionModel.from_config(synth.TINY_UNET_CONFIG, precision=precision).to(CPU)
+    plain.load_state_dict(synth.synth_state_dict(synth.unet_param_shapes(synth.TINY_UNET_CONFIG), seed=0))
+    with pytest.raises(L.TangoB200Error):          # and Tango's blocks take none
+        plain(tt("sample"), 3, tt("ehs"), beat_features=tt("beat"), chord_features=tt("chord"))
