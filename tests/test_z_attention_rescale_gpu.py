@@ -8,6 +8,7 @@ from test_kernels_gpu import attn_ref, bf, rel_err, to_split
 
 pytestmark = pytest.mark.gpu
 
+@pytest.mark.xfail(strict=False, reason="not yet run on hardware: written after the round's GPU budget was spent (logic checked on the CPU against the C-ABI contract); XPASS = validated")
 @pytest.mark.parametrize("nsplit", [1, 2])
 def test_attention_growing_scores_take_the_rescale_path(cuda, nsplit):
     """Key magnitudes ramp up along the sequence, so the running row maximum outgrows the lazy-rescale threshold (2^8)
