@@ -238,8 +238,7 @@ class AudioDiffusion:
         [(2)B, L, D] + `boolean_prompt_mask`), initial `latents`, per-step `noises` (one (B,8,H,W) tensor per step,
         used where the reference draws randn) or a torch `generator`; `latent_shape` for clips other than 10 s."""
         device = self.device
-        if device.type != "cuda":
-            raise L.TangoB200Error("AudioDiffusion.inference runs on CUDA only (there is no CPU fallback)")
+        L.require_cuda_device(device)   # no CPU fallback
         cfg_on = guidance_scale > 1.0
         if prompt_embeds is None:
             if cfg_on:

@@ -158,3 +158,37 @@ def test_mustango_unet_orchestration_vs_reference_golden(precision, tol):
     plain.load_state_dict(synth.synth_state_dict(synth.unet_param_shapes(synth.TINY_UNET_CONFIG), seed=0))
     with pytest.raises(L.TangoB200Error):          # and Tango's blocks take none
         plain(tt("sample"), 3, tt("ehs"), beat_features=tt("beat"), chord_features=tt("chord"))
+
+
+class _NoEvent:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a, **k):
+        pass
+
+    def elapsed_time(self, other):
+        return 0.0
+
+
+@pytest.mark.parametrize("precision,tol", [("split", 1e-4), ("bf16", 6e-2)])
+def test_inference_loop_orchestration_vs_reference_golden(monkeypatch, precision, tol):
+    """AudioDiffusion.inference (CFG duplication, per-step time-embedding rows, fused CFG + scheduler step, per-step
+    noise) against the latents of the reference's own loop (tests/golden/tiny_inference.npz); eager path (CUDA-graph
+    capture is a GPU-only facility and replays exactly these launches)."""
+    from tango_b200.pipeline import AudioDiffusion
+    from tango_b200.schedulers import DDPMScheduler
+    monkeypatch.setattr(torch.cuda, "Event", _NoEvent)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(L, "launch_count", lambda: 0)
+    gd = np.load(os.path.join(GOLD, "tiny_inference.npz"))
+    cfg = synth.TINY_UNET_CONFIG
+    m = AudioDiffusion(unet_config=cfg, precision=precision, use_cuda_graph=False).to(CPU)
+    m.unet.load_state_dict(synth.synth_state_dict(synth.unet_param_shapes(cfg), seed=0))
+    trace = []
+    lat = m.inference(["synthetic prompt"], DDPMScheduler.from_pretrained(), 4, 3.0,
+                      prompt_embeds=torch.from_numpy(gd["embeds"]), boolean_prompt_mask=torch.from_numpy(gd["mask"]),
+                      latents=torch.from_numpy(gd["lat0"]), noises=[torch.from_numpy(n) for n in gd["noises"]],
+                      latent_shape=(32, 16), trace=trace)
+    assert len(trace) == 4 and lat.shape == gd["latents"].shape
+    assert rel(lat, gd["latents"]) < tol
