@@ -15,13 +15,15 @@ from . import unet as ounet
 
 
 def inference(unet_sd, unet_cfg, scheduler, prompt_embeds, mask, num_steps, guidance_scale, latents0,
-              noises: Optional[List[torch.Tensor]] = None, trace: Optional[list] = None):
+              noises: Optional[List[torch.Tensor]] = None, trace: Optional[list] = None, extra_streams=()):
+    """`extra_streams`: the Mustango loop (mustango/models.py:540-600, MusicAudioDiffusion.inference) is this same loop
+    with the (already CFG-duplicated) encoded beats and chords handed to the UNet at every step."""
     cfg = guidance_scale > 1.0
     scheduler.set_timesteps(num_steps)
     latents = latents0 * scheduler.init_noise_sigma
     for i, t in enumerate(scheduler.timesteps):
         x = torch.cat([latents] * 2) if cfg else latents
-        pred = ounet.unet_forward(unet_sd, unet_cfg, x, t, prompt_embeds, mask)
+        pred = ounet.unet_forward(unet_sd, unet_cfg, x, t, prompt_embeds, mask, extra_streams=extra_streams)
         if cfg:
             u, c = pred.chunk(2)
             pred = u + guidance_scale * (c - u)

@@ -233,10 +233,12 @@ class AudioDiffusion:
                   disable_progress=True, *, prompt_embeds: Optional[torch.Tensor] = None,
                   boolean_prompt_mask: Optional[torch.Tensor] = None, latents: Optional[torch.Tensor] = None,
                   noises: Optional[Sequence[torch.Tensor]] = None, generator=None, latent_shape=LATENT_HW,
-                  trace: Optional[list] = None) -> torch.Tensor:
+                  trace: Optional[list] = None, extra_streams=()) -> torch.Tensor:
         """models.py:210-257. Extra keyword-only arguments (all optional): inject conditioning (`prompt_embeds`
         [(2)B, L, D] + `boolean_prompt_mask`), initial `latents`, per-step `noises` (one (B,8,H,W) tensor per step,
-        used where the reference draws randn) or a torch `generator`; `latent_shape` for clips other than 10 s."""
+        used where the reference draws randn) or a torch `generator`; `latent_shape` for clips other than 10 s;
+        `extra_streams` = ((encoded beats [(2)B, L, D], mask), (encoded chords, mask)) turns the loop into Mustango's
+        MusicAudioDiffusion.inference (mustango/models.py:540-600; needs a UNet config with the *Music blocks)."""
         device = self.device
         L.require_cuda_device(device)   # no CPU fallback
         cfg_on = guidance_scale > 1.0
@@ -261,7 +263,7 @@ class AudioDiffusion:
         sample = latents.contiguous().clone()
 
         unet = self.unet
-        unet.set_conditioning(prompt_embeds, boolean_prompt_mask)
+        unet.set_conditioning(prompt_embeds, boolean_prompt_mask, extra_streams=extra_streams)
         tkey = (id(unet.P),) + tuple(sch._t_list)   # unet.P is rebuilt when weights are (re)loaded
         if self._temb_cache.get("key") != tkey:   # batch- and data-independent: reuse across calls with the same grid
             self._temb_cache = {"key": tkey, "table": unet.time_embedding_table(timesteps)}
@@ -269,7 +271,8 @@ class AudioDiffusion:
         coef = sch.coefficient_table(device)                          # [steps, 10]
         s = unet.s
         HW = H * W
-        key = (Bu, H, W, prompt_embeds.shape[1], boolean_prompt_mask is not None)
+        key = (Bu, H, W, prompt_embeds.shape[1], boolean_prompt_mask is not None) + \
+            tuple((f.shape[1], m is not None) for f, m in extra_streams)
         st = self._state.get(key)
         if st is None:
             st = SimpleNamespace(

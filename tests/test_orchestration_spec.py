@@ -192,3 +192,33 @@ def test_inference_loop_orchestration_vs_reference_golden(monkeypatch, precision
                       latent_shape=(32, 16), trace=trace)
     assert len(trace) == 4 and lat.shape == gd["latents"].shape
     assert rel(lat, gd["latents"]) < tol
+
+
+def test_mustango_inference_loop_vs_oracle(monkeypatch):
+    """MusicAudioDiffusion.inference (mustango/models.py:540-600) = the Tango loop with encoded beats / chords handed to
+    the Music UNet at every step; checked against the oracle loop (its UNet is pinned to the fork's Music UNet, its loop
+    to the reference's Tango loop)."""
+    from oracle import pipeline as opipe
+    from oracle import schedulers as osched
+    from tango_b200.pipeline import AudioDiffusion
+    from tango_b200.schedulers import DDPMScheduler
+    monkeypatch.setattr(torch.cuda, "Event", _NoEvent)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(L, "launch_count", lambda: 0)
+    cfg = synth.TINY_MUSIC_UNET_CONFIG
+    sd = synth.synth_state_dict(synth.unet_param_shapes(cfg), seed=0)
+    B, steps, guidance, D = 1, 3, 3.0, cfg["cross_attention_dim"]
+    embeds, mask = synth.synth_conditioning(B, 9, D, seed=5, masked_tail=2)
+    g = torch.Generator().manual_seed(31)
+    beats, chords = torch.randn(2 * B, 6, D, generator=g), torch.randn(2 * B, 4, D, generator=g)
+    bmask = torch.ones(2 * B, 6, dtype=torch.bool)
+    bmask[0, 1:] = False
+    streams = ((beats, bmask), (chords, None))
+    lat0, noises = synth.synth_noise(B, steps, shape=(8, 32, 16), seed=7)
+    want = opipe.inference(sd, cfg, osched.OracleDDPM(**osched.SD21_CONFIG), embeds, mask, steps, guidance, lat0, noises,
+                           extra_streams=streams)
+    m = AudioDiffusion(unet_config=cfg, precision="split", use_cuda_graph=False).to(CPU)
+    m.unet.load_state_dict(sd)
+    lat = m.inference(["x"], DDPMScheduler.from_pretrained(), steps, guidance, prompt_embeds=embeds,
+                      boolean_prompt_mask=mask, latents=lat0, noises=noises, latent_shape=(32, 16), extra_streams=streams)
+    assert rel(lat, want) < 1e-4
