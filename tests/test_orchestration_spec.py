@@ -222,3 +222,43 @@ def test_mustango_inference_loop_vs_oracle(monkeypatch):
     lat = m.inference(["x"], DDPMScheduler.from_pretrained(), steps, guidance, prompt_embeds=embeds,
                       boolean_prompt_mask=mask, latents=lat0, noises=noises, latent_shape=(32, 16), extra_streams=streams)
     assert rel(lat, want) < 1e-4
+
+
+def test_tango_generate_prompt_to_waveform_vs_oracle(monkeypatch):
+    """Tango.generate / generate_for_batch (tango.py:43-64) end to end on the tiny architecture: prompt -> synthetic text
+    states -> CFG loop -> VAE decoder -> HiFi-GAN -> int16, against the oracle pipeline on the same conditioning and
+    noise. Also the DDIM / no-CFG branch (models.py:214,218-221)."""
+    from oracle import hifigan as ohifi
+    from oracle import pipeline as opipe
+    from oracle import schedulers as osched
+    from oracle import vae as ovae
+    from tango_b200.pipeline import Tango
+    monkeypatch.setattr(torch.cuda, "Event", _NoEvent)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(L, "launch_count", lambda: 0)
+    cfg = synth.TINY_UNET_CONFIG
+    t = Tango.from_synthetic(unet_config=cfg, device="cpu", precision="split")
+    t.model.use_cuda_graph = False
+    prompts = ["a dog barking in the rain", "church bells"]
+    lat0, noises = synth.synth_noise(2, 3, shape=(8, 32, 16), seed=11)
+    waves = t.generate_for_batch(prompts, steps=3, guidance=3, batch_size=2, latent_shape=(32, 16), latents=lat0,
+                                 noises=noises)
+    assert len(waves) == 2 and all(w.dtype == np.int16 and w.shape == (20512,) for w in waves)
+    # the oracle on the same conditioning
+    pe, pm = t.model.encode_text_classifier_free(prompts, 1)
+    usd = synth.synth_state_dict(synth.unet_param_shapes(cfg), 0)
+    vsd = synth.synth_state_dict(synth.vae_decoder_param_shapes(), 0)
+    lat = opipe.inference(usd, cfg, osched.OracleDDPM(**osched.SD21_CONFIG), pe, pm, 3, 3.0, lat0, noises)
+    mel = ovae.decode_first_stage(vsd, lat, synth.VAE_CONFIG["scale_factor"])
+    wref, wi_ref = ohifi.decode_to_waveform(vsd, mel)
+    got = np.stack(waves).astype(np.int32)
+    assert np.abs(got - wi_ref.astype(np.int32)).max() <= 64            # ~2e-3 of full scale through loop + decode
+    one = t.generate(prompts[0], steps=2, guidance=3, latent_shape=(32, 16))
+    assert one.dtype == np.int16 and one.shape == (20512,)
+    # DDIM, guidance <= 1: no CFG duplication
+    from tango_b200.schedulers import DDIMScheduler
+    pe1, pm1 = t.model.encode_text(prompts)
+    l1 = t.model.inference(prompts, DDIMScheduler.from_pretrained(None), 3, 1.0, prompt_embeds=pe1,
+                           boolean_prompt_mask=pm1, latents=lat0, latent_shape=(32, 16))
+    w1 = opipe.inference(usd, cfg, osched.OracleDDIM(**osched.SD21_CONFIG), pe1, pm1, 3, 1.0, lat0)
+    assert rel(l1, w1) < 1e-4
