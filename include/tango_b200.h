@@ -219,6 +219,22 @@ int tng_convt_gather(const float* Y, int64_t B, int64_t Lin, int32_t ktaps, int6
  * (C-style truncation toward zero; the +1.0 wrap-around of the reference is reproduced). */
 int tng_tanh_to_i16(const float* x, int64_t n, int64_t ld_x, float* wave_f32, int16_t* wave_i16, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * TacotronSTFT mel front-end: audioldm/audio/stft.py:52-83 (STFT.transform: reflect pad,
+ * strided conv1d with the windowed Fourier basis, magnitude), :161-186 (mel_spectrogram), audio_processing.py:85-91
+ * (log of the value clamped at 1e-5). The two contractions (basis, mel filter bank) run through tng_conv_gemm.
+ * tng_stft_frames: y fp32 [B, T] -> reflect-padded by `pad` on both sides, split into bf16 hi / lo planes [B, ld]
+ *   (ld >= T + 2 pad, zero beyond): frame f of batch b is the OVERLAPPING window [f hop, f hop + filter_length) of a plane,
+ *   i.e. a tng_aview with s_w = hop — the conv1d needs no im2col buffer.
+ * tng_stft_magnitude: F fp32 [rows, ldF] = (real | imag) halves of `bins` columns -> mag = sqrt(re^2 + im^2) as the bf16
+ *   operand of the mel GEMM (hi at column b, lo at split_off + b; may be NULL), log_mag fp32 [rows, bins] =
+ *   log(max(mag, floor)) (may be NULL), energy fp32 [rows] = ||mag||_2 (may be NULL).
+ * tng_log_clamp: y = log(max(x, floor)). */
+int tng_stft_frames(const float* y, int64_t B, int64_t T, int32_t pad, void* hi, void* lo, int64_t ld, void* stream);
+int tng_stft_magnitude(const float* F, int64_t rows, int32_t bins, int64_t ldF, void* mag_op, int64_t ld_op,
+                       int32_t split_off, float* log_mag, float* energy, float floor_v, void* stream);
+int tng_log_clamp(const float* x, int64_t n, float floor_v, float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

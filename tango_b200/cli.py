@@ -108,7 +108,9 @@ def main(argv: Optional[Sequence[str]] = None) -> dict:
             dist.broadcast(t, 0)
             args.exp_id = str(int(t.item()))
     if args.seed is not None:
-        torch.manual_seed(args.seed + rank)
+        # the SAME seed on every rank: each rank draws the full-batch noise and keeps its rows, so an N-GPU run produces
+        # the waveforms of the one-GPU run (AudioDiffusion.randn_rows)
+        torch.manual_seed(args.seed)
 
     prompts = read_prompts(args.test_file, args.text_key)
     exp_id = args.exp_id or str(int(time.time()))
@@ -116,27 +118,28 @@ def main(argv: Optional[Sequence[str]] = None) -> dict:
     os.makedirs(out_dir, exist_ok=True)
 
     tango = build_tango(args.checkpoint, device, args.precision, args.scheduler)
-    lo, hi = parallel.shard_range(len(prompts), rank, world)
     kw = {} if args.latent_h == 256 else {"latent_shape": (args.latent_h, 16)}
     torch.cuda.synchronize()
     t0 = time.time()
-    waves = tango.generate_for_batch(prompts[lo:hi], steps=args.num_steps, guidance=args.guidance,
-                                     batch_size=args.batch_size, **kw)
+    # every chunk of batch_size prompts is split over the ranks; all ranks end up with all waveforms
+    waves = tango.generate_for_batch(prompts, steps=args.num_steps, guidance=args.guidance,
+                                     batch_size=args.batch_size, shard=world > 1, **kw)
     torch.cuda.synchronize()
     gen_s = time.time() - t0
     for j, wav in enumerate(waves):
-        write_wav(os.path.join(out_dir, "output_{}.wav".format(lo + j)), wav)
+        if j % world == rank:                     # the file writes are spread over the ranks
+            write_wav(os.path.join(out_dir, "output_{}.wav".format(j)), wav)
     if world > 1:
         gen_s = parallel.max_over_ranks(gen_s, device)
     audio_s = sum(len(w) for w in waves) / 16000.0
-    if world > 1:
-        audio_s = parallel.sum_over_ranks(audio_s, device)
 
     result = {"Steps": args.num_steps, "Guidance Scale": args.guidance, "Test Instances": len(prompts),
               "scheduler_config": dict(tango.scheduler.config), "args": dict(vars(args)), "output_dir": out_dir,
               "n_gpus": world, "generation_seconds": gen_s, "audio_seconds": audio_s,
               "audio_seconds_per_second": audio_s / max(gen_s, 1e-9),
               "text_encoder": "synthetic" if getattr(tango.model.text_encoder, "synthetic", False) else "t5",
+              "tokenizer": "synthetic" if getattr(getattr(tango.model, "tokenizer", None), "synthetic", False) else
+                           ("n/a" if getattr(tango.model, "tokenizer", None) is None else "t5"),
               "metrics": "not computed here: score output_dir with audioldm_eval as inference_hf.py:111 does"}
     if rank == 0:
         with open(os.path.join(args.output_root, "tango_checkpoint_summary.jsonl"), "a") as f:

@@ -1,25 +1,12 @@
 // attention_tc.cu — tcgen05 flash attention for head width 64 (UNet self- and cross-attention), sm_100a.
 //
-// Two kernels share the data layout (one CTA = 128 query rows of one (batch, head), thread r of the softmax warps owns
-// query row r = TMEM lane r; Q / K / V arrive as TMA SWIZZLE_128B tiles; S and O live in TMEM; K-major A/B operands
-// straight from the TMA tiles, V consumed as an MN-major B operand, no transpose; two CTAs per SM in perf mode):
-//   * attention_sub_kernel (default): warp-specialised (4 softmax warps + 1 loader/MMA-issuer warp), software-pipelined
-//     over 64-key sub-tiles with S double-buffered in TMEM, single-pass softmax against a lazily advanced reference
-//     maximum, P handed to the P V MMA through tensor memory (tcgen05.st + TS-mode MMA), three K/V tile buffers.
-//     See the comment above the kernel.
-//   * attention_tc_kernel (TNG_ATTN=2; the round-1 baseline kept for A/B measurements): tile-at-a-time, described next.
-// Per 128-key tile j:
-//   S = Q K_j^T    tcgen05.mma 128x128x16, K-major A/B straight from TMA SWIZZLE_128B tiles, fp32 S in TMEM
-//   softmax        pass 1: row max of the raw scores (tcgen05.ld); pass 2: p = exp2(s*scale*log2e - m) -> bf16 ->
-//                  swizzled smem (the A operand of the next MMA); row sum in fp32. The reference max m is only
-//                  advanced when the row max grew by more than 2^8 ("lazy rescale"), so the common tile does no
-//                  correction work at all.
-//   O += P V_j     tcgen05.mma 128x64x16 accumulating IN TMEM (V consumed as an MN-major B operand, no transpose)
-// When the reference max does move, the warp rescales its O rows in place (tcgen05.ld -> scale -> tcgen05.st).
-// Issue order on the tensor pipe is  P V_j , Q K_{j+1}^T  back to back right after the softmax of tile j, so the
-// S-ready barrier of tile j+1 also certifies that P V_j has drained (P smem and O are safe to touch).
-// Resources are sized for TWO CTAs per SM (112 KB smem, 256 TMEM columns): while one CTA is in its softmax the other
-// one's MMAs keep the tensor pipe busy. K/V tiles are double-buffered and TMA-prefetched one tile ahead.
+// One CTA = 128 query rows of one (batch, head); thread r of the softmax warps owns query row r = TMEM lane r; Q / K / V
+// arrive as TMA SWIZZLE_128B tiles; S, P and O live in TMEM; K-major A/B operands straight from the TMA tiles, V consumed
+// as an MN-major B operand (no transpose); two CTAs per SM in perf mode. attention_sub_kernel is warp-specialised
+// (4 softmax warps + 1 loader / MMA-issuer warp) and software-pipelined over 64-key sub-tiles with S double-buffered in
+// TMEM, single-pass softmax against a lazily advanced reference maximum ("lazy rescale": the reference max only moves when
+// a row grew by more than 2^8), P handed to the P V MMA through tensor memory (tcgen05.st + TS-mode MMA), three K/V tile
+// buffers. See the comment above the kernel.
 // NSPLIT = 2 is the parity mode: every operand carries its bf16 rounding residual and each product is evaluated as
 // hi*hi + lo*hi + hi*lo, which restores ~fp32 accuracy on the bf16 tensor cores (1 CTA / SM).
 #include "tng_ptx.cuh"
@@ -54,326 +41,9 @@ struct AttnCfg {
   static constexpr int TMEM_COLS = 256;                   // S: 128, O: 64
 };
 
-template <int NSPLIT>
-__global__ void __launch_bounds__(128, (NSPLIT == 1) ? 2 : 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
-                    const __grid_constant__ CUtensorMap vmap, const __grid_constant__ AttnParams p) {
-  using Cfg = AttnCfg<NSPLIT>;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Cfg::Q_BYTES;                 // [NBUF][KV_BYTES]
-  uint8_t* sV = sK + AT_NBUF * Cfg::KV_BYTES;      // [NBUF][KV_BYTES]
-  uint8_t* sP = sV + AT_NBUF * Cfg::KV_BYTES;      // hi chunks 0,1 then lo chunks 0,1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
-  uint64_t* bar_q = bars;             // [1]
-  uint64_t* bar_kv = bars + 1;        // [NBUF]
-  uint64_t* bar_s = bars + 1 + AT_NBUF;  // [1]  S_j ready (and P V_{j-1} drained)
-  uint64_t* bar_o = bars + 2 + AT_NBUF;  // [1]  final P V drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + AT_NBUF);
-  float* sbias = reinterpret_cast<float*>(sP + Cfg::P_BYTES + 128);  // per-tile key bias (log2 domain), -inf = masked
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int q0 = blockIdx.x * AT_BM;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int n_tiles = (p.Lk + AT_BN - 1) / AT_BN;
-
-  if (tid == 0) {
-    if ((smem_u32(smem) & 1023u) != 0) {
-      printf("[tng] attention: dynamic smem base not 1024-byte aligned\n");
-      __trap();
-    }
-    tma_prefetch_desc(&qmap);
-    tma_prefetch_desc(&kmap);
-    tma_prefetch_desc(&vmap);
-    mbar_init(bar_q, 1);
-    for (int i = 0; i < AT_NBUF; ++i) mbar_init(&bar_kv[i], 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_o, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    __syncwarp();
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_s = tmem_base;
-  const uint32_t tm_o = tmem_base + 128;
-
-  auto load_kv = [&](int tile) {
-    const int buf = tile % AT_NBUF;
-    mbar_arrive_expect_tx(&bar_kv[buf], 2 * Cfg::KV_BYTES);
-    const int kv0 = tile * AT_BN;
-#pragma unroll
-    for (int s = 0; s < NSPLIT; ++s) {
-      tma_load_3d(sK + buf * Cfg::KV_BYTES + s * AT_CHUNK, &kmap, &bar_kv[buf], p.k_col0 + s * p.k_lo_off + head * AT_D,
-                  kv0, b);
-      tma_load_3d(sV + buf * Cfg::KV_BYTES + s * AT_CHUNK, &vmap, &bar_kv[buf], p.v_col0 + s * p.v_lo_off + head * AT_D,
-                  kv0, b);
-    }
-  };
-  // S = Q K_tile^T  (hi*hi [+ lo*hi + hi*lo]); arrives on bar_s when it (and everything issued before) is done
-  auto issue_qk = [&](int tile) {
-    const int buf = tile % AT_NBUF;
-    constexpr uint32_t idesc = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
-    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + buf * Cfg::KV_BYTES);
-    constexpr int NT = (NSPLIT == 1) ? 1 : 3;
-    const int qsel[3] = {0, 1, 0}, ksel[3] = {0, 0, 1};
-    uint32_t acc = 0;
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      const uint64_t adesc = umma_desc_sw128(qa + qsel[t] * AT_CHUNK, 16, 1024);
-      const uint64_t bdesc = umma_desc_sw128(ka + ksel[t] * AT_CHUNK, 16, 1024);
-#pragma unroll
-      for (int k = 0; k < AT_D / 16; ++k) {
-        umma_bf16(tm_s, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-        acc = 1;
-      }
-    }
-    umma_commit(bar_s);
-  };
-  // O (+)= P V_tile   (A = P K-major chunks, B = V MN-major: 16 keys per MMA = 2 swizzle atoms = 2048 B)
-  auto issue_pv = [&](int tile, uint32_t accumulate, int nk16) {
-    const int buf = tile % AT_NBUF;
-    constexpr uint32_t idesc = umma_idesc_bf16(AT_BM, AT_D, 0, 1);
-    const uint32_t pa = smem_u32(sP), va = smem_u32(sV + buf * Cfg::KV_BYTES);
-    constexpr int NT = (NSPLIT == 1) ? 1 : 3;
-    const int psel[3] = {0, 1, 0}, vsel[3] = {0, 0, 1};
-    uint32_t acc = accumulate;
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-#pragma unroll
-      for (int k = 0; k < AT_BN / 16; ++k) {
-        if (k >= nk16) break;  // keys beyond the written P columns (short last tile)
-        const uint64_t adesc =
-            umma_desc_sw128(pa + psel[t] * 2 * AT_CHUNK + (k >> 2) * AT_CHUNK, 16, 1024) + 2 * (k & 3);
-        const uint64_t bdesc = umma_desc_sw128(va + vsel[t] * AT_CHUNK + k * 2048, 1024, 1024);
-        umma_bf16(tm_o, adesc, bdesc, idesc, acc);
-        acc = 1;
-      }
-    }
-  };
-
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, Cfg::Q_BYTES);
-#pragma unroll
-    for (int s = 0; s < NSPLIT; ++s)
-      tma_load_3d(sQ + s * AT_CHUNK, &qmap, bar_q, p.q_col0 + s * p.q_lo_off + head * AT_D, q0, b);
-    for (int t = 0; t < AT_NBUF && t < n_tiles; ++t) load_kv(t);
-    mbar_wait(bar_q, 0);
-    mbar_wait(&bar_kv[0], 0);
-    tc_fence_after();
-    issue_qk(0);
-  }
-
-  const int r = tid;  // query row owned by this thread == TMEM lane
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-  const uint32_t ts = tm_s + lane_addr;
-  const uint32_t to = tm_o + lane_addr;
-  float m_ref = -INFINITY;  // reference max used in the exponent (log2 domain)
-  float l_run = 0.f;
-  const float sc = p.scale_log2e;
-  const float* kb = p.kbias ? p.kbias + static_cast<long long>(b) * p.Lk : nullptr;
-  constexpr float LOG2E = 1.4426950408889634f;
-  uint8_t* prow_base = sP + r * 128;
-  const int rsw = r & 7;
-
-  for (int j = 0; j < n_tiles; ++j) {
-    __syncwarp();
-    mbar_wait(bar_s, j & 1);   // S_j complete; in-order tensor pipe => P V_{j-1} complete as well
-    tc_fence_after();
-    // K/V buffer of tile j-1 is free now: prefetch tile j+1 into it (tile j+1 == (j-1) + NBUF)
-    if (tid == 0 && j >= 1 && j + 1 < n_tiles) load_kv(j + 1);
-    const int kv0 = j * AT_BN;
-    const bool tail = (kb != nullptr) || (kv0 + AT_BN > p.Lk);
-    // columns actually processed in this tile (multiple of 32); P columns beyond are never written nor multiplied
-    const int ncols = tail ? min(AT_BN, ((p.Lk - kv0) + 31) & ~31) : AT_BN;
-    if (tail) {
-      // one bias value per key of the tile, shared through smem: additive mask bias (already * log2e) or -inf
-      // for keys beyond Lk -> the softmax passes below need no per-element predicates or global loads
-      const int kv = kv0 + tid;
-      float bv = -INFINITY;
-      if (kv < p.Lk) bv = kb ? kb[kv] * LOG2E : 0.f;
-      __syncthreads();  // previous tile's readers are done
-      sbias[tid] = bv;
-      __syncthreads();
-    }
-    // ---- pass 1: row maximum (log2 domain)
-    float m_tile = -INFINITY;
-    if (!tail) {
-#pragma unroll 1
-      for (int c = 0; c < AT_BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(ts + c, v);
-        tmem_ld_wait();
-        // four independent max chains (a single serial chain of 128 dependent FMNMX costs ~4 cycles each)
-        float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
-#pragma unroll
-        for (int i = 4; i < 32; i += 4) {
-          m0 = fmaxf(m0, __uint_as_float(v[i]));
-          m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
-          m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
-          m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
-        }
-        m_tile = fmaxf(m_tile, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-      }
-      m_tile *= sc;  // scale > 0
-    } else {
-#pragma unroll 1
-      for (int c = 0; c < ncols; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(ts + c, v);
-        tmem_ld_wait();
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          m0 = fmaxf(m0, fmaf(__uint_as_float(v[i]), sc, sbias[c + i]));
-          m1 = fmaxf(m1, fmaf(__uint_as_float(v[i + 1]), sc, sbias[c + i + 1]));
-          m2 = fmaxf(m2, fmaf(__uint_as_float(v[i + 2]), sc, sbias[c + i + 2]));
-          m3 = fmaxf(m3, fmaf(__uint_as_float(v[i + 3]), sc, sbias[c + i + 3]));
-        }
-        m_tile = fmaxf(m_tile, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-      }
-    }
-    // ---- lazy rescale of the running state (warp-uniform decision; tcgen05.ld/st are warp collectives)
-    const bool need = m_tile > m_ref + AT_LAZY;
-    if (__any_sync(0xffffffffu, need)) {
-      const float m_new = need ? m_tile : m_ref;
-      const float f = (j == 0) ? 0.f : ex2_approx(m_ref - m_new);  // 1 for rows that keep their reference
-      l_run *= f;
-      if (j > 0) {
-#pragma unroll
-        for (int c = 0; c < AT_D; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(to + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-          tmem_st32(to + c, v);
-        }
-        tmem_st_wait();
-      }
-      m_ref = m_new;
-    }
-    // ---- pass 2: probabilities -> bf16 (hi/lo) -> swizzled smem
-#pragma unroll 1
-    for (int c = 0; c < ncols; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(ts + c, v);
-      tmem_ld_wait();
-      float pr[32];
-      if (!tail) {
-        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;  // independent partial sums (ILP)
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -m_ref));
-          pr[i + 1] = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -m_ref));
-          pr[i + 2] = ex2_approx(fmaf(__uint_as_float(v[i + 2]), sc, -m_ref));
-          pr[i + 3] = ex2_approx(fmaf(__uint_as_float(v[i + 3]), sc, -m_ref));
-          l0 += pr[i]; l1 += pr[i + 1]; l2 += pr[i + 2]; l3 += pr[i + 3];
-        }
-        l_run += (l0 + l1) + (l2 + l3);
-      } else {
-        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sc, sbias[c + i]) - m_ref);       // ex2(-inf) = 0 for masked keys
-          pr[i + 1] = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, sbias[c + i + 1]) - m_ref);
-          pr[i + 2] = ex2_approx(fmaf(__uint_as_float(v[i + 2]), sc, sbias[c + i + 2]) - m_ref);
-          pr[i + 3] = ex2_approx(fmaf(__uint_as_float(v[i + 3]), sc, sbias[c + i + 3]) - m_ref);
-          l0 += pr[i]; l1 += pr[i + 1]; l2 += pr[i + 2]; l3 += pr[i + 3];
-        }
-        l_run += (l0 + l1) + (l2 + l3);
-      }
-      uint8_t* prow = prow_base + (c >> 6) * AT_CHUNK;
-      const int u0 = (c & 63) >> 3;  // first 16-byte unit inside the 128-byte row
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        uint4 w;
-        w.x = pack_bf16(pr[8 * u + 0], pr[8 * u + 1]);
-        w.y = pack_bf16(pr[8 * u + 2], pr[8 * u + 3]);
-        w.z = pack_bf16(pr[8 * u + 4], pr[8 * u + 5]);
-        w.w = pack_bf16(pr[8 * u + 6], pr[8 * u + 7]);
-        *reinterpret_cast<uint4*>(prow + (((u0 + u) ^ rsw) << 4)) = w;
-        if (NSPLIT == 2) {
-          float lo[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) lo[q] = pr[8 * u + q] - __bfloat162float(__float2bfloat16_rn(pr[8 * u + q]));
-          uint4 wl;
-          wl.x = pack_bf16(lo[0], lo[1]); wl.y = pack_bf16(lo[2], lo[3]);
-          wl.z = pack_bf16(lo[4], lo[5]); wl.w = pack_bf16(lo[6], lo[7]);
-          *reinterpret_cast<uint4*>(prow + 2 * AT_CHUNK + (((u0 + u) ^ rsw) << 4)) = wl;
-        }
-      }
-    }
-    // P (generic-proxy writes) must be visible to the tensor core (async proxy); all S reads / O rescales are done.
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_pv(j, j > 0 ? 1u : 0u, ncols / 16);
-      if (j + 1 < n_tiles) {
-        mbar_wait(&bar_kv[(j + 1) % AT_NBUF], ((j + 1) / AT_NBUF) & 1);
-        tc_fence_after();
-        issue_qk(j + 1);       // commits bar_s after P V_j and Q K_{j+1}^T
-      } else {
-        umma_commit(bar_o);
-      }
-    }
-  }
-
-  // ---- finalize: O / l -> bf16 (hi/lo)
-  __syncwarp();
-  mbar_wait(bar_o, 0);
-  tc_fence_after();
-  const int q = q0 + r;
-  const float inv = 1.0f / l_run;
-  __nv_bfloat16* op = p.out + (static_cast<long long>(b) * p.Lq + q) * p.ld_o + head * AT_D;
-#pragma unroll
-  for (int c = 0; c < AT_D; c += 32) {
-    uint32_t v[32];
-    tmem_ld32(to + c, v);
-    tmem_ld_wait();
-    if (q < p.Lq) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        float y[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(v[i + t]) * inv;
-        uint4 w;
-        w.x = pack_bf16(y[0], y[1]); w.y = pack_bf16(y[2], y[3]);
-        w.z = pack_bf16(y[4], y[5]); w.w = pack_bf16(y[6], y[7]);
-        *reinterpret_cast<uint4*>(op + c + i) = w;
-        if (p.split_off > 0) {
-          float lo[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) lo[t] = y[t] - __bfloat162float(__float2bfloat16_rn(y[t]));
-          uint4 wl;
-          wl.x = pack_bf16(lo[0], lo[1]); wl.y = pack_bf16(lo[2], lo[3]);
-          wl.z = pack_bf16(lo[4], lo[5]); wl.w = pack_bf16(lo[6], lo[7]);
-          *reinterpret_cast<uint4*>(op + p.split_off + c + i) = wl;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  }
-}
-
-
 // =====================================================================================================================
-// attention_sub_kernel — same data layout and occupancy as attention_tc_kernel (thread = query row, two CTAs per SM in
-// perf mode), but warp-specialised and software-pipelined at 64-key SUB-TILE granularity inside the CTA:
+// attention_sub_kernel — thread = query row, two CTAs per SM in perf mode, warp-specialised and software-pipelined at
+// 64-key SUB-TILE granularity inside the CTA:
 //   * warps 0-3 (128 threads) only do softmax; warp 4 (one elected lane) owns TMA loads and every tcgen05.mma. The
 //     main loop has no CTA-wide barrier: softmax -> issuer through bar_p (128 arrivals: "P_g is in smem and S_g has
 //     been read"), issuer -> softmax through tcgen05.commit barriers;
@@ -819,23 +489,6 @@ static int launch_attn_sub(const tng_attn_desc* d, const CUtensorMap& qm, const 
   return check_launch("attention_sub");
 }
 
-template <int NSPLIT>
-static int launch_attn(const tng_attn_desc* d, const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm,
-                       const AttnParams& p, cudaStream_t st) {
-  using Cfg = AttnCfg<NSPLIT>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return set_error(TNG_ECUDA, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
-    attr = true;
-  }
-  dim3 grid((d->Lq + AT_BM - 1) / AT_BM, d->heads, d->batch);
-  attention_tc_kernel<NSPLIT><<<grid, 128, Cfg::SMEM_BYTES, st>>>(qm, km, vm, p);
-  count_launch();
-  return check_launch("attention_tc");
-}
-
 }  // namespace tng
 
 using namespace tng;
@@ -877,16 +530,6 @@ extern "C" int tng_attention(const tng_attn_desc* d, void* stream) {
     if (rc) return rc;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // TNG_ATTN=2 selects the older tile-at-a-time kernel (kept for A/B measurements); TNG_ATTN_VAR=3 hands P to the
-  // P V MMA through shared memory (two K/V buffers) instead of tensor memory (three K/V buffers, default)
-  static int variant = -1, var = -1;
-  if (variant < 0) { const char* e = getenv("TNG_ATTN"); variant = e ? atoi(e) : 4; }
-  if (var < 0) { const char* e = getenv("TNG_ATTN_VAR"); var = e ? atoi(e) : 6; }
-  if (d->nsplit == 2) {
-    if (variant == 2) return launch_attn<2>(d, qm, km, vm, p, st);
-    return var == 3 ? launch_attn_sub<2, 3>(d, qm, km, vm, p, st) : launch_attn_sub<2, 6>(d, qm, km, vm, p, st);
-  }
-  if (variant == 2) return launch_attn<1>(d, qm, km, vm, p, st);
-  if (var == 3) return launch_attn_sub<1, 3>(d, qm, km, vm, p, st);
+  if (d->nsplit == 2) return launch_attn_sub<2, 6>(d, qm, km, vm, p, st);
   return launch_attn_sub<1, 6>(d, qm, km, vm, p, st);
 }

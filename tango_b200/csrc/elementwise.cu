@@ -552,6 +552,59 @@ __global__ void tanh_to_i16_kernel(const float* x, long long n, long long ld_x, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ STFT front-end
+// y fp32 [B, T] -> reflect-padded (F.pad mode="reflect": no edge repeat) bf16 hi / lo planes [B, ld]; positions past
+// T + 2*pad are zero. The frames of STFT.transform are then an OVERLAPPING strided view of these planes.
+__global__ void __launch_bounds__(256) stft_frames_kernel(const float* y, long long B, long long T, int pad,
+                                                           __nv_bfloat16* hi, __nv_bfloat16* lo, long long ld) {
+  const long long total = B * ld;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / ld, j = i % ld;
+    float v = 0.f;
+    if (j < T + 2 * pad) {
+      long long src = j - pad;
+      if (src < 0) src = -src;
+      else if (src >= T) src = 2 * (T - 1) - src;
+      v = y[b * T + src];
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// One warp per frame: F [rows, ldF] = (real[0..bins) | imag[0..bins)) -> magnitude (bf16 hi/lo GEMM operand),
+// log(max(mag, floor)) and the l2 norm over the bins (stft.py:74-77,178-184; audio_processing.py:85-91).
+__global__ void __launch_bounds__(256) stft_magnitude_kernel(const float* F, long long rows, int bins, long long ldF,
+                                                              __nv_bfloat16* op, long long ld_op, int split_off,
+                                                              float* log_mag, float* energy, float floor_v) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* f = F + row * ldF;
+  float e = 0.f;
+  for (int b = lane; b < bins; b += 32) {
+    const float re = f[b], im = f[bins + b];
+    const float m = sqrtf(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+    e = fmaf(m, m, e);
+    if (op) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(m);
+      op[row * ld_op + b] = h;
+      if (split_off > 0) op[row * ld_op + split_off + b] = __float2bfloat16_rn(m - __bfloat162float(h));
+    }
+    if (log_mag) log_mag[row * bins + b] = logf(fmaxf(m, floor_v));
+  }
+  e = warp_sum(e);
+  if (energy && lane == 0) energy[row] = sqrtf(e);
+}
+
+__global__ void __launch_bounds__(256) log_clamp_kernel(const float* x, long long n, float floor_v, float* y) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = logf(fmaxf(x[i], floor_v));
+}
+
 // pixels per GroupNorm CTA: enough CTAs (>= 4 per SM) even on the small-spatial levels
 static inline int gn_rows_for(long long NB, long long HW) {
   long long rows = (NB * HW + 4LL * num_sms() - 1) / (4LL * num_sms());
@@ -748,4 +801,31 @@ extern "C" int tng_tanh_to_i16(const float* x, int64_t n, int64_t ld_x, float* w
   tanh_to_i16_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(x, n, ld_x, wave_f32, wave_i16);
   count_launch();
   return check_launch("tanh_to_i16");
+}
+
+extern "C" int tng_stft_frames(const float* y, int64_t B, int64_t T, int32_t pad, void* hi, void* lo, int64_t ld,
+                               void* stream) {
+  if (!y || !hi || !lo || B <= 0 || T <= pad || pad < 0 || ld < T + 2 * pad)
+    return set_error(TNG_EINVAL, "stft_frames: bad argument (reflect padding needs T > pad)");
+  stft_frames_kernel<<<grid_for(B * ld), 256, 0, ST(stream)>>>(y, B, T, pad, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                reinterpret_cast<__nv_bfloat16*>(lo), ld);
+  count_launch();
+  return check_launch("stft_frames");
+}
+
+extern "C" int tng_stft_magnitude(const float* F, int64_t rows, int32_t bins, int64_t ldF, void* mag_op, int64_t ld_op,
+                                  int32_t split_off, float* log_mag, float* energy, float floor_v, void* stream) {
+  if (!F || rows <= 0 || bins <= 0 || ldF < 2 * bins) return set_error(TNG_EINVAL, "stft_magnitude: bad argument");
+  const int wpb = 8;
+  stft_magnitude_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, ST(stream)>>>(
+      F, rows, bins, ldF, reinterpret_cast<__nv_bfloat16*>(mag_op), ld_op, split_off, log_mag, energy, floor_v);
+  count_launch();
+  return check_launch("stft_magnitude");
+}
+
+extern "C" int tng_log_clamp(const float* x, int64_t n, float floor_v, float* y, void* stream) {
+  if (!x || !y || n <= 0) return set_error(TNG_EINVAL, "log_clamp: bad argument");
+  log_clamp_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(x, n, floor_v, y);
+  count_launch();
+  return check_launch("log_clamp");
 }

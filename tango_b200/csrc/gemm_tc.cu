@@ -57,7 +57,6 @@ struct GemmKernelParams {
   int split_off;
   int vec_ok;    // all row strides / bases allow 16-byte vector access
   int fast_epi;  // vec_ok && Ncols % 4 == 0
-  int dbg;       // TNG_GEMM_DBG: 1 = skip epilogue body, 2 = TMEM loads only (profiling experiments)
 };
 
 // PAIR: cta_group::2 — each CTA of the pair stages its own 128 A rows and only HALF of the weight tile
@@ -572,12 +571,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
-          if (p.dbg == 3) {  // experiment: A only (results are garbage)
-            mbar_arrive_expect_tx(&full_bar[stage], A_TILE_BYTES);
-            tma_load_4d(sA + stage * A_TILE_BYTES, am, &full_bar[stage], g.a_c0 + kb * BK, w0 + g.dw, h0 + g.dh, n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            continue;
-          }
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_4d(sA + stage * A_TILE_BYTES, am, &full_bar[stage], g.a_c0 + kb * BK, w0 + g.dw, h0 + g.dh, n0);
           if (CL == 1) {
@@ -594,9 +587,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     }
   } else if (warp == 1 && lane == 0 && (!PAIR || crank == 0)) {
     // ===================================================== MMA issuer (pair mode: leader CTA only)
-    constexpr uint32_t idesc_full = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN, 0, 0);
-    constexpr uint32_t idesc_half = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN >= 128 ? 128 : BN, 0, 0);
-    const uint32_t idesc = (p.dbg == 4) ? idesc_half : idesc_full;  // dbg 4: N = 128 MMAs on the same loads
+    constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -657,18 +648,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       tc_fence_after();
       if (tm >= p.m_tiles) nvalid = 0;  // padding tile of an odd cluster tail
       const bool full = p.fast_epi && (nvalid == BM) && ((tn + 1) * BN <= p.Ncols);
-      if (p.dbg == 1) {
-        // experiment: no epilogue work at all
-      } else if (p.dbg == 3 || p.dbg == 4) {
-        // experiments on the main loop: no epilogue work
-      } else if (p.dbg == 2) {
-        for (int c = hf * 32; c < BN; c += 64) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c, v);
-          tmem_ld_wait();
-          if (v[0] == 0x7fc12345u && v[7] == 0x12345u) st[lane] = __uint_as_float(v[3]);
-        }
-      } else if (p.ksplit > 1) {
+      if (p.ksplit > 1) {
         epi_tile_splitk<BN>(p, st, row_base, n0, rpi, nvalid, sp, taddr, tn, lane, ew, hf);
       } else if (geglu) {
         // slot i of this lane is row ew*32 + rsub + 4i; rows below nvalid are valid
@@ -873,11 +853,6 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   if (d->out_bf16 && (!al16(d->out_bf16) || d->ld_bf16 % 8 || d->split_off % 8)) vec = false;
   p.vec_ok = vec ? 1 : 0;
   p.fast_epi = (vec && d->Ncols % 4 == 0) ? 1 : 0;
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("TNG_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
-    p.dbg = dbg;
-  }
   if ((d->act == TNG_ACT_GEGLU || d->act == TNG_ACT_GEGLU_TANH) && !vec) return set_error(TNG_EINVAL, "GEGLU epilogue needs 16-byte aligned output");
 
   // cluster of 2 CTAs along M sharing (multicasting) the weight tile: whenever there are at least two M tiles

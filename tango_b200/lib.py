@@ -23,7 +23,8 @@ SYMBOLS = [
     "tng_version", "tng_last_error", "tng_launch_count", "tng_conv_gemm", "tng_attention",
     "tng_groupnorm_stats", "tng_groupnorm_apply", "tng_layernorm", "tng_cast_act", "tng_softmax_rows",
     "tng_transpose_bf16", "tng_sched_step", "tng_timestep_embedding", "tng_linear_f32", "tng_convt_gather",
-    "tng_tanh_to_i16", "tng_rmsnorm", "tng_gather_rows", "tng_rel_attention",
+    "tng_tanh_to_i16", "tng_rmsnorm", "tng_gather_rows", "tng_rel_attention", "tng_stft_frames", "tng_stft_magnitude",
+    "tng_log_clamp",
 ]
 
 
@@ -105,6 +106,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "tng_linear_f32": [vp, i64, i64, vp, vp, i64, i32, i32, vp, vp],
         "tng_convt_gather": [vp, i64, i64, i32, i64, i32, i32, i64, vp, vp, vp],
         "tng_tanh_to_i16": [vp, i64, i64, vp, vp, vp],
+        "tng_stft_frames": [vp, i64, i64, i32, vp, vp, i64, vp],
+        "tng_stft_magnitude": [vp, i64, i32, i64, vp, i64, i32, vp, vp, f32, vp],
+        "tng_log_clamp": [vp, i64, f32, vp, vp],
     }
     for name, argt in sigs.items():
         fn = getattr(lib, name)
@@ -139,6 +143,7 @@ class _Profiler:
         return out
 
     def timed(self, family, flops, nbytes, fn):
+        """Run fn() (one kernel launch); when profiling, bracket it with CUDA events on the current stream."""
         if not self.enabled:
             return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -151,14 +156,19 @@ class _Profiler:
 
 PROF = _Profiler()
 
-# profiling experiments only (tools/ablate.py): TNG_SKIP=gn,ln,attn,gemm makes the named launches no-ops
-_SKIP = set(filter(None, os.environ.get("TNG_SKIP", "").split(",")))
-
-
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().tng_last_error().decode("utf-8", "replace")
         raise TangoB200Error(f"{what or 'tng call'} failed ({rc}): {msg}")
+
+
+def _call(family: str, nbytes: float, fn, *args) -> None:
+    """One C-ABI launch; `nbytes` = its algorithmic HBM bytes (bench.py's per-family HBM roofline)."""
+    PROF.timed(family, 0.0, nbytes, lambda: check(fn(*args), family))
+
+
+def _esz(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.element_size()
 
 
 def launch_count() -> int:
@@ -217,8 +227,6 @@ def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tens
               rowvec_ld: int = 0, algo_k: Optional[int] = None) -> None:
     """Launch tng_conv_gemm. groups: (view, a_c0, dw, dh, b_k0, nkb). weight: bf16 [Ncols, Ktot].
     algo_k: algorithmic reduction length (taps * Cin of the reference op) for the profiler's FLOP count."""
-    if "gemm" in _SKIP:
-        return
     lib = load()
     d = GemmDesc()
     require_cuda(weight, bias, rowvec, res, out_f32, out_bf16)
@@ -263,8 +271,6 @@ def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tens
 
 def attention(q, k, v, out, *, batch, heads, Lq, Lk, scale, q_col0=0, k_col0=0, v_col0=0, kbias=None, nsplit=1,
               q_lo_off=0, k_lo_off=0, v_lo_off=0, split_off=0) -> None:
-    if "attn" in _SKIP:
-        return
     lib = load()
     require_cuda(q, k, v, out, kbias)
     d = AttnDesc()
@@ -281,28 +287,26 @@ def attention(q, k, v, out, *, batch, heads, Lq, Lk, scale, q_col0=0, k_col0=0, 
 # --------------------------------------------------------------------------------------------------- norms etc.
 def groupnorm(x0, x1, NB, HW, groups, stats, gamma, beta, eps, act, y, *, split_off=0, raw=None, raw_split_off=0):
     """GroupNorm(+act) of the channel concat [x0 | x1] (x1 may be None) -> bf16 y; optional raw bf16 copy."""
-    if "gn" in _SKIP:
-        return
     lib = load()
     require_cuda(x0, x1, stats, gamma, beta, y, raw)
     C0 = x0.shape[-1]
     C1 = 0 if x1 is None else x1.shape[-1]
     s = stream_ptr()
-    check(lib.tng_groupnorm_stats(x0.data_ptr(), _dt(x0), C0, ptr(x1), 0 if x1 is None else _dt(x1), C1, NB, HW,
-                                  groups, stats.data_ptr(), s), "tng_groupnorm_stats")
-    check(lib.tng_groupnorm_apply(x0.data_ptr(), _dt(x0), C0, ptr(x1), 0 if x1 is None else _dt(x1), C1, NB, HW,
-                                  groups, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, act,
-                                  y.data_ptr(), y.stride(0), split_off, ptr(raw),
-                                  0 if raw is None else raw.stride(0), raw_split_off, s), "tng_groupnorm_apply")
+    rows = NB * HW
+    in_bytes = rows * (C0 * _esz(x0) + C1 * _esz(x1))
+    _call("gn_stats", in_bytes, lib.tng_groupnorm_stats, x0.data_ptr(), _dt(x0), C0, ptr(x1),
+          0 if x1 is None else _dt(x1), C1, NB, HW, groups, stats.data_ptr(), s)
+    out_bytes = rows * (C0 + C1) * 2 * (2 if split_off else 1) * (2 if raw is not None else 1)
+    _call("gn_apply", in_bytes + out_bytes, lib.tng_groupnorm_apply, x0.data_ptr(), _dt(x0), C0, ptr(x1),
+          0 if x1 is None else _dt(x1), C1, NB, HW, groups, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps,
+          act, y.data_ptr(), y.stride(0), split_off, ptr(raw), 0 if raw is None else raw.stride(0), raw_split_off, s)
 
 
 def layernorm(x, gamma, beta, eps, y, *, split_off=0):
-    if "ln" in _SKIP:
-        return
     require_cuda(x, gamma, beta, y)
     rows, Cc = x.shape
-    check(load().tng_layernorm(x.data_ptr(), rows, Cc, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(),
-                               y.stride(0), split_off, stream_ptr()), "tng_layernorm")
+    _call("layernorm", rows * Cc * (4 + (4 if split_off else 2)), load().tng_layernorm, x.data_ptr(), rows, Cc,
+          gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(), y.stride(0), split_off, stream_ptr())
 
 
 def rmsnorm(x, gamma, eps, y=None, *, split_off=0, y_f32=None):
@@ -331,30 +335,33 @@ def rel_attention(qkv, relbias, kbias, out, *, batch, heads, L, q_col0, k_col0, 
 def cast_act(x, NB, H, W, y, *, Cc=None, upsample2x=False, act=ACT_NONE, act_param=0.0, split_off=0):
     require_cuda(x, y)
     Cc = x.shape[-1] if Cc is None else Cc
-    check(load().tng_cast_act(x.data_ptr(), NB, H, W, Cc, x.stride(0), int(upsample2x), act, act_param, y.data_ptr(),
-                              y.stride(0), split_off, stream_ptr()), "tng_cast_act")
+    n_out = NB * H * W * (4 if upsample2x else 1) * Cc
+    _call("cast_act", NB * H * W * Cc * 4 + n_out * (4 if split_off else 2), load().tng_cast_act, x.data_ptr(), NB, H,
+          W, Cc, x.stride(0), int(upsample2x), act, act_param, y.data_ptr(), y.stride(0), split_off, stream_ptr())
 
 
 def softmax_rows(x, scale, y, *, L=None, split_off=0):
     require_cuda(x, y)
     rows = x.shape[0]
     L = x.shape[1] if L is None else L
-    check(load().tng_softmax_rows(x.data_ptr(), rows, L, x.stride(0), scale, y.data_ptr(), y.stride(0), split_off,
-                                  stream_ptr()), "tng_softmax_rows")
+    _call("softmax_rows", rows * L * (4 + (4 if split_off else 2)), load().tng_softmax_rows, x.data_ptr(), rows, L,
+          x.stride(0), scale, y.data_ptr(), y.stride(0), split_off, stream_ptr())
 
 
 def transpose_bf16(x, B, R, Cc, y):
     require_cuda(x, y)
-    check(load().tng_transpose_bf16(x.data_ptr(), B, R, Cc, x.stride(0), y.data_ptr(), y.stride(0), stream_ptr()),
-          "tng_transpose_bf16")
+    _call("transpose_bf16", B * R * Cc * 4, load().tng_transpose_bf16, x.data_ptr(), B, R, Cc, x.stride(0),
+          y.data_ptr(), y.stride(0), stream_ptr())
 
 
 def sched_step(model_out, cfg, guidance, sample, noise, coef, prev, next_in, *, B, Cc, HW, split_off=0):
     require_cuda(model_out, sample, noise, coef, prev, next_in)
-    check(load().tng_sched_step(ptr(model_out), 0 if model_out is None else model_out.stride(0), int(cfg), guidance,
-                                sample.data_ptr(), ptr(noise), coef.data_ptr(), ptr(prev), ptr(next_in),
-                                0 if next_in is None else next_in.stride(0), split_off, B, Cc, HW, stream_ptr()),
-          "tng_sched_step")
+    n = B * Cc * HW
+    nbytes = n * 4 * ((2 if cfg else 1) * (model_out is not None) + 1 + (noise is not None) + (prev is not None)) \
+        + (0 if next_in is None else n * (2 if cfg else 1) * (4 if split_off else 2))
+    _call("sched_step", nbytes, load().tng_sched_step, ptr(model_out), 0 if model_out is None else model_out.stride(0),
+          int(cfg), guidance, sample.data_ptr(), ptr(noise), coef.data_ptr(), ptr(prev), ptr(next_in),
+          0 if next_in is None else next_in.stride(0), split_off, B, Cc, HW, stream_ptr())
 
 
 def timestep_embedding(t, dim, flip_sin_to_cos, freq_shift, out):
@@ -373,11 +380,31 @@ def linear_f32(x, w, b, y, *, pre_act=ACT_NONE, post_act=ACT_NONE):
 
 def convt_gather(Y, B, Lin, ktaps, Cout, stride, pad, Lout, bias, y):
     require_cuda(Y, bias, y)
-    check(load().tng_convt_gather(Y.data_ptr(), B, Lin, ktaps, Cout, stride, pad, Lout, ptr(bias), y.data_ptr(),
-                                  stream_ptr()), "tng_convt_gather")
+    _call("convt_gather", (B * Lin * ktaps * Cout + B * Lout * Cout) * 4, load().tng_convt_gather, Y.data_ptr(), B, Lin,
+          ktaps, Cout, stride, pad, Lout, ptr(bias), y.data_ptr(), stream_ptr())
 
 
 def tanh_to_i16(x, n, ld_x, wave_f32, wave_i16):
     require_cuda(x, wave_f32, wave_i16)
-    check(load().tng_tanh_to_i16(x.data_ptr(), n, ld_x, ptr(wave_f32), ptr(wave_i16), stream_ptr()),
-          "tng_tanh_to_i16")
+    _call("tanh_to_i16", n * (4 + (4 if wave_f32 is not None else 0) + (2 if wave_i16 is not None else 0)),
+          load().tng_tanh_to_i16, x.data_ptr(), n, ld_x, ptr(wave_f32), ptr(wave_i16), stream_ptr())
+
+
+def stft_frames(y, pad, hi, lo):
+    require_cuda(y, hi, lo)
+    B, T = y.shape
+    _call("stft_frames", B * T * 4 + 2 * hi.numel() * 2, load().tng_stft_frames, y.data_ptr(), B, T, pad, hi.data_ptr(),
+          lo.data_ptr(), hi.stride(0), stream_ptr())
+
+
+def stft_magnitude(F, bins, mag_op, split_off, log_mag, energy, floor=1e-5):
+    require_cuda(F, mag_op, log_mag, energy)
+    rows = F.shape[0]
+    _call("stft_magnitude", rows * bins * (8 + 4 + 4), load().tng_stft_magnitude, F.data_ptr(), rows, bins, F.stride(0),
+          ptr(mag_op), 0 if mag_op is None else mag_op.stride(0), split_off, ptr(log_mag), ptr(energy), floor,
+          stream_ptr())
+
+
+def log_clamp(x, y, floor=1e-5):
+    require_cuda(x, y)
+    _call("log_clamp", x.numel() * 8, load().tng_log_clamp, x.data_ptr(), x.numel(), floor, y.data_ptr(), stream_ptr())

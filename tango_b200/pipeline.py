@@ -21,7 +21,9 @@ from __future__ import annotations
 
 import json
 import os
+import warnings
 import zlib
+from collections import OrderedDict
 from types import SimpleNamespace
 from typing import List, Optional, Sequence
 
@@ -32,6 +34,7 @@ from . import lib as L
 from . import parallel
 from . import synth
 from .schedulers import DDIMScheduler, DDPMScheduler
+from .stft import TacotronSTFT
 from .t5 import T5EncoderModel
 from .unet import UNet2DConditionModel
 from .vae import AutoencoderKL
@@ -107,7 +110,8 @@ class AudioDiffusion:
 
     def __init__(self, text_encoder_name=None, scheduler_name=None, unet_model_name=None,
                  unet_model_config_path=None, snr_gamma=None, freeze_text_encoder=True, uncondition=False,
-                 unet_config: Optional[dict] = None, precision: str = "bf16", use_cuda_graph: bool = True):
+                 unet_config: Optional[dict] = None, precision: str = "bf16", use_cuda_graph: bool = True,
+                 allow_synthetic_tokenizer: bool = False):
         assert unet_model_config_path is not None or unet_config is not None or unet_model_name is not None, \
             "Either UNet pretrain model name or a config file path is required"
         if unet_model_name is not None and unet_config is None and unet_model_config_path is None:
@@ -126,15 +130,27 @@ class AudioDiffusion:
         self.device = torch.device("cpu")
         self.tokenizer = None
         self.text_encoder = None
+        self.allow_synthetic_tokenizer = allow_synthetic_tokenizer   # tests / synthetic weights only (see below)
         self._uncond_cache = {}
-        self._state = {}
+        self._state = OrderedDict()   # captured CUDA graphs + their persistent I/O buffers, LRU-bounded
         self._temb_cache = {}
         self.last_step_ms: Optional[float] = None
         self.last_kernel_launches = 0
         self.launches_per_forward = 0
 
     # ------------------------------------------------------------------------------------------ module plumbing
+    MAX_GRAPHS = 8      # distinct (batch, clip length, padded text length, ...) shapes kept captured
+    LK_BUCKET = 32      # masked text lengths are padded up to a multiple of this (one graph per bucket, not per length)
+
+    def _invalidate(self):
+        """Captured graphs hold raw pointers into the UNet's packed weights and scratch buffers: drop them whenever
+        those are rebuilt (new weights, new device)."""
+        self._state.clear()
+        self._temb_cache = {}
+
     def to(self, device):
+        if torch.device(device) != self.device:
+            self._invalidate()
         self.device = torch.device(device)
         self.unet.to(self.device)
         if self.text_encoder is not None and hasattr(self.text_encoder, "to"):
@@ -148,6 +164,7 @@ class AudioDiffusion:
         """pytorch_model_main.bin holds `unet.*` and `text_encoder.*` keys (tango.py:28)."""
         unet_sd = {k[len("unet."):]: v for k, v in sd.items() if k.startswith("unet.")}
         self.unet.load_state_dict(unet_sd, strict=strict)
+        self._invalidate()
         te = {k[len("text_encoder."):]: v for k, v in sd.items() if k.startswith("text_encoder.")}
         if te:
             self.set_text_encoder_state_dict(te)
@@ -173,7 +190,16 @@ class AudioDiffusion:
             try:
                 from transformers import AutoTokenizer
                 self.tokenizer = AutoTokenizer.from_pretrained(name, local_files_only=True)
-            except Exception:
+            except Exception as e:
+                # A real FLAN-T5 encoder fed with hashed token ids produces meaningless conditioning: refuse unless the
+                # caller opted in (tests and seeded random weights, where the ids carry no meaning anyway).
+                if not self.allow_synthetic_tokenizer:
+                    raise L.TangoB200Error(
+                        f"the FLAN-T5 tokenizer of '{name}' is not available locally ({type(e).__name__}: {e}); pass a "
+                        "snapshot directory that contains its SentencePiece files, or construct AudioDiffusion with "
+                        "allow_synthetic_tokenizer=True (synthetic weights / tests only)") from e
+                warnings.warn("tango_b200: using the hashed stand-in tokenizer (FallbackTokenizer): token ids are NOT "
+                              "FLAN-T5's — only meaningful with synthetic weights", stacklevel=2)
                 self.tokenizer = FallbackTokenizer(self.text_encoder.cfg["vocab_size"])
 
     # ------------------------------------------------------------------------------------------ text (boundary input)
@@ -220,11 +246,40 @@ class AudioDiffusion:
         pm = torch.cat([nam, am]).to(self.device)
         return pe, (pm == 1)
 
+    @staticmethod
+    def randn_rows(shape, generator, device, dtype=torch.float32, rows=None) -> torch.Tensor:
+        """The seed contract of diffusers' `randn_tensor` (D/utils/torch_utils.py:29-70) plus the sharding rule of
+        SURVEY.md section 8e. `generator`: None (global torch RNG), one torch.Generator, or a LIST with one generator
+        per sample — then every sample is drawn on its own as a (1, ...) tensor and the draws are concatenated
+        (torch_utils.py:60-66), which makes a sample's noise independent of batch size, chunking and GPU count.
+        `rows` = (lo, hi, total): this process holds samples [lo, hi) of a `total`-sample batch. With a single
+        generator the FULL (total, ...) tensor is drawn and sliced, so that every rank (same seed) sees exactly the
+        stream a one-GPU run would; with a per-sample list only the local generators [lo, hi) are consumed."""
+        lo, hi, total = (0, shape[0], shape[0]) if rows is None else rows
+        if hi - lo != shape[0]:
+            raise ValueError(f"rows={rows} does not match a local batch of {shape[0]}")
+        if isinstance(generator, (list, tuple)):
+            if len(generator) == 1:
+                generator = generator[0]
+            elif len(generator) == total:
+                generator = list(generator[lo:hi])
+            elif len(generator) != shape[0]:
+                raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an "
+                                 f"effective batch size of {total}. Make sure the batch size matches the length of "
+                                 "the generators.")
+        if isinstance(generator, (list, tuple)):
+            one = (1,) + tuple(shape[1:])
+            parts = [torch.randn(one, generator=g, device=g.device, dtype=dtype).to(device) for g in generator]
+            return torch.cat(parts, dim=0)
+        gdev = device if generator is None else generator.device
+        full = torch.randn((total,) + tuple(shape[1:]), generator=generator, device=gdev, dtype=dtype).to(device)
+        return full if (lo == 0 and hi == total) else full[lo:hi].contiguous()
+
     def prepare_latents(self, batch_size, inference_scheduler, num_channels_latents, dtype, device, generator=None,
-                        latent_shape=LATENT_HW):
+                        latent_shape=LATENT_HW, rows=None):
         """models.py:259-264."""
         shape = (batch_size, num_channels_latents, *latent_shape)
-        latents = torch.randn(shape, generator=generator, device=device, dtype=dtype)
+        latents = self.randn_rows(shape, generator, device, dtype, rows)
         return latents * inference_scheduler.init_noise_sigma
 
     # ------------------------------------------------------------------------------------------ the hot loop
@@ -233,10 +288,12 @@ class AudioDiffusion:
                   disable_progress=True, *, prompt_embeds: Optional[torch.Tensor] = None,
                   boolean_prompt_mask: Optional[torch.Tensor] = None, latents: Optional[torch.Tensor] = None,
                   noises: Optional[Sequence[torch.Tensor]] = None, generator=None, latent_shape=LATENT_HW,
-                  trace: Optional[list] = None, extra_streams=()) -> torch.Tensor:
+                  trace: Optional[list] = None, extra_streams=(), noise_rows=None) -> torch.Tensor:
         """models.py:210-257. Extra keyword-only arguments (all optional): inject conditioning (`prompt_embeds`
         [(2)B, L, D] + `boolean_prompt_mask`), initial `latents`, per-step `noises` (one (B,8,H,W) tensor per step,
-        used where the reference draws randn) or a torch `generator`; `latent_shape` for clips other than 10 s;
+        used where the reference draws randn) or a torch `generator` (or a list with one generator per sample, as
+        diffusers' randn_tensor accepts); `noise_rows` = (lo, hi, total) when this process holds samples [lo, hi) of a
+        `total`-sample batch sharded over GPUs (see randn_rows); `latent_shape` for clips other than 10 s;
         `extra_streams` = ((encoded beats [(2)B, L, D], mask), (encoded chords, mask)) turns the loop into Mustango's
         MusicAudioDiffusion.inference (mustango/models.py:540-600; needs a UNet config with the *Music blocks)."""
         device = self.device
@@ -257,24 +314,37 @@ class AudioDiffusion:
         Cl = self.unet.config["in_channels"]
         H, W = latent_shape
         if latents is None:
-            latents = self.prepare_latents(batch_size, sch, Cl, torch.float32, device, generator, latent_shape)
+            latents = self.prepare_latents(batch_size, sch, Cl, torch.float32, device, generator, latent_shape,
+                                           rows=noise_rows)
         else:
             latents = latents.to(device, torch.float32) * sch.init_noise_sigma
         sample = latents.contiguous().clone()
 
         unet = self.unet
+        if boolean_prompt_mask is not None and prompt_embeds.shape[1] % self.LK_BUCKET:
+            # pad the text length up to the bucket: masked keys get the reference's -10000 bias (exp underflows to
+            # exactly 0 in fp32), so the result is unchanged while real traffic needs one graph per bucket, not per length
+            pad = self.LK_BUCKET - prompt_embeds.shape[1] % self.LK_BUCKET
+            prompt_embeds = torch.nn.functional.pad(prompt_embeds, (0, 0, 0, pad))
+            boolean_prompt_mask = torch.nn.functional.pad(boolean_prompt_mask.to(torch.bool), (0, pad), value=False)
         unet.set_conditioning(prompt_embeds, boolean_prompt_mask, extra_streams=extra_streams)
-        tkey = (id(unet.P),) + tuple(sch._t_list)   # unet.P is rebuilt when weights are (re)loaded
+        tkey = (unet.pack_generation, str(device)) + tuple(sch._t_list)   # packed weights are rebuilt on (re)load
         if self._temb_cache.get("key") != tkey:   # batch- and data-independent: reuse across calls with the same grid
             self._temb_cache = {"key": tkey, "table": unet.time_embedding_table(timesteps)}
         temb_table = self._temb_cache["table"]                      # [steps, temb_total]
         coef = sch.coefficient_table(device)                          # [steps, 10]
         s = unet.s
         HW = H * W
-        key = (Bu, H, W, prompt_embeds.shape[1], boolean_prompt_mask is not None) + \
-            tuple((f.shape[1], m is not None) for f, m in extra_streams)
+        # cfg_on is part of the key: the captured forward bakes in cfg_shared (the CFG shared prefix); so are the device
+        # and the generation of the packed weights the graph points into
+        key = (Bu, H, W, prompt_embeds.shape[1], boolean_prompt_mask is not None, bool(cfg_on), str(device),
+               unet.pack_generation) + tuple((f.shape[1], m is not None) for f, m in extra_streams)
         st = self._state.get(key)
+        if st is not None:
+            self._state.move_to_end(key)
         if st is None:
+            while len(self._state) >= self.MAX_GRAPHS:
+                self._state.popitem(last=False)
             st = SimpleNamespace(
                 x_in=torch.zeros(Bu * HW, Cl * s, device=device, dtype=torch.bfloat16),
                 model_out=torch.zeros(Bu * HW, unet.config["out_channels"], device=device, dtype=torch.float32),
@@ -322,7 +392,7 @@ class AudioDiffusion:
                 if noises is not None:
                     noise = noises[i].to(device, torch.float32).contiguous()
                 else:
-                    noise = torch.randn((batch_size, Cl, H, W), generator=generator, device=device, dtype=torch.float32)
+                    noise = self.randn_rows((batch_size, Cl, H, W), generator, device, torch.float32, noise_rows)
             L.sched_step(model_out, cfg_on, float(guidance_scale), sample, noise, coef[i], sample, x_in, B=batch_size,
                          Cc=Cl, HW=HW, split_off=so)
             if trace is not None:
@@ -347,21 +417,27 @@ class Tango:
                 f"'{name}' is not a local checkpoint directory. The reference downloads it from the Hugging Face hub "
                 "(tango.py:12); offline, pass the directory of a downloaded snapshot or use Tango.from_synthetic().")
         vae_config = json.load(open(f"{path}/vae_config.json"))
+        stft_config = json.load(open(f"{path}/stft_config.json"))
         main_config = json.load(open(f"{path}/main_config.json"))
         if unet_config_path is not None:
             main_config["unet_model_config_path"] = unet_config_path
-        self._init_modules(vae_config, main_config, device, precision)
+        self._init_modules(vae_config, main_config, device, precision, stft_config=stft_config)
         self.vae.load_state_dict(torch.load(f"{path}/pytorch_model_vae.bin", map_location="cpu"))
+        self.stft.load_state_dict(torch.load(f"{path}/pytorch_model_stft.bin", map_location="cpu"))
         self.model.load_state_dict(torch.load(f"{path}/pytorch_model_main.bin", map_location="cpu"))
         print("Successfully loaded checkpoint from:", name)
 
-    def _init_modules(self, vae_config, main_config, device, precision, unet_config=None):
+    def _init_modules(self, vae_config, main_config, device, precision, unet_config=None, stft_config=None,
+                      allow_synthetic_tokenizer: bool = False):
         self.device = torch.device(device)
         self.vae = AutoencoderKL(**vae_config, precision=precision).to(device)
-        self.stft = None  # TacotronSTFT is only loaded, never used, at inference (tango.py:19) — "next" row
+        # tango.py:19,23,27 — read by inference.py:81 / inference_hf.py:77 (tango.stft): the mel front-end on the kernels
+        self.stft = TacotronSTFT(**(stft_config or synth.STFT_CONFIG)).to(device)
         mc = {k: v for k, v in main_config.items()}
-        self.model = AudioDiffusion(**mc, unet_config=unet_config, precision=precision).to(device)
+        self.model = AudioDiffusion(**mc, unet_config=unet_config, precision=precision,
+                                    allow_synthetic_tokenizer=allow_synthetic_tokenizer).to(device)
         self.vae.eval()
+        self.stft.eval()
         self.model.eval()
         self.scheduler = DDPMScheduler.from_pretrained(main_config.get("scheduler_name"), subfolder="scheduler")
 
@@ -374,7 +450,8 @@ class Tango:
         self = cls.__new__(cls)
         ucfg = dict(unet_config or synth.BASE_UNET_CONFIG)
         self._init_modules(dict(synth.VAE_CONFIG), {"scheduler_name": "stabilityai/stable-diffusion-2-1",
-                                                    "text_encoder_name": None}, device, precision, unet_config=ucfg)
+                                                    "text_encoder_name": None}, device, precision, unet_config=ucfg,
+                           allow_synthetic_tokenizer=True)
         self.model.unet.load_state_dict(synth.synth_state_dict(synth.unet_param_shapes(ucfg), seed))
         self.vae.load_state_dict(synth.synth_state_dict(synth.vae_decoder_param_shapes(), seed))
         if scheduler == "ddim":
@@ -409,23 +486,32 @@ class Tango:
 
     def generate_for_batch(self, prompts, steps=100, guidance=3, samples=1, batch_size=8, disable_progress=True,
                            shard: bool = False, **kw):
-        """ Genrate audio for a list of prompt strings. With `shard=True` under torch.distributed the prompts are
-        split contiguously over the ranks and rank 0 receives every waveform (other ranks return their own)."""
-        my = list(prompts)
-        lo = 0
-        if shard and parallel.world_size() > 1:
-            lo, hi = parallel.shard_range(len(prompts), parallel.rank(), parallel.world_size())
-            my = list(prompts[lo:hi])
+        """ Genrate audio for a list of prompt strings. With `shard=True` under torch.distributed every chunk of
+        `batch_size` prompts is split contiguously over the ranks and every rank returns all
+        waveforms. The noise of a sharded run equals that of the one-GPU run on the same seed: each rank draws the
+        chunk's full-batch tensors from its (identically seeded) generator and keeps its rows, or consumes only its own
+        entries of a per-sample `generator` list (AudioDiffusion.randn_rows; diffusers torch_utils.py:29-70)."""
+        prompts = list(prompts)
+        world, r = (parallel.world_size(), parallel.rank()) if shard else (1, 0)
+        gens = kw.pop("generator", None)
+        per_sample = isinstance(gens, (list, tuple)) and len(gens) > 1
+        if per_sample and len(gens) != len(prompts) * samples:
+            raise ValueError(f"a per-sample generator list needs {len(prompts) * samples} entries, got {len(gens)}")
         outputs = []
-        for k in range(0, len(my), batch_size):
-            batch = my[k: k + batch_size]
-            with torch.no_grad():
-                latents = self.model.inference(batch, self.scheduler, steps, guidance, samples,
-                                               disable_progress=disable_progress, **kw)
-                wave = self._decode(latents)
-                outputs += [item for item in wave]
-        if shard and parallel.world_size() > 1:
-            outputs = parallel.gather_waves(outputs, dst=0)
+        for k in range(0, len(prompts), batch_size):
+            batch = prompts[k: k + batch_size]
+            lo, hi = parallel.shard_range(len(batch), r, world)
+            g = list(gens[k * samples:(k + len(batch)) * samples]) if per_sample else gens
+            wave = np.zeros((0, 0), dtype=np.int16)
+            if hi > lo:
+                rows = (lo * samples, hi * samples, len(batch) * samples) if world > 1 else None
+                with torch.no_grad():
+                    latents = self.model.inference(batch[lo:hi], self.scheduler, steps, guidance, samples,
+                                                   disable_progress=disable_progress, generator=g, noise_rows=rows, **kw)
+                    wave = self._decode(latents)
+            if world > 1:
+                wave = parallel.allgather_waves(wave, self.device)
+            outputs += [item for item in wave]
         if samples == 1:
             return outputs
         return list(self.chunks(outputs, samples))

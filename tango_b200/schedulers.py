@@ -66,8 +66,24 @@ class _SchedulerBase:
 
     @classmethod
     def from_pretrained(cls, name: str = "stabilityai/stable-diffusion-2-1", subfolder: str = "scheduler", **overrides):
-        """The reference downloads the SD-2.1 scheduler JSON from the hub; offline we use its published values."""
+        """The reference downloads the SD-2.1 scheduler JSON from the hub (tango.py:36, models.py:80-81). Offline:
+        a local directory is read (`<name>/<subfolder>/scheduler_config.json` or `<name>/scheduler_config.json`);
+        `stabilityai/stable-diffusion-2-1` (or None) maps to its published values; any other name is refused rather
+        than silently sampled with the wrong betas / prediction type."""
+        import json
+        import os
         base = dict(SD21_SCHEDULER_CONFIG)
+        if name is not None and os.path.isdir(str(name)):
+            for cand in (os.path.join(name, subfolder or "", "scheduler_config.json"), os.path.join(name, "scheduler_config.json")):
+                if os.path.exists(cand):
+                    with open(cand) as f:
+                        base.update({k: v for k, v in json.load(f).items() if not k.startswith("_")})
+                    break
+            else:
+                raise FileNotFoundError(f"no scheduler_config.json under '{name}'")
+        elif name not in (None, "stabilityai/stable-diffusion-2-1"):
+            raise ValueError(f"scheduler '{name}' is not reachable offline: pass a local directory holding its "
+                             "scheduler_config.json (only stabilityai/stable-diffusion-2-1 is built in)")
         base.update(overrides)
         return cls(**{k: v for k, v in base.items() if k in cls._ACCEPTED})
 

@@ -43,6 +43,10 @@ VAE_CONFIG = {"image_key": "fbank", "subband": 1, "embed_dim": 8, "time_shuffle"
                            "attn_resolutions": [], "dropout": 0.0},
               "scale_factor": 0.9227914214134216}
 
+# stft_config.json of the declare-lab/tango checkpoints (tango.py:15)
+STFT_CONFIG = {"filter_length": 1024, "hop_length": 160, "win_length": 1024, "n_mel_channels": 64,
+               "sampling_rate": 16000, "mel_fmin": 0, "mel_fmax": 8000}
+
 HIFIGAN_CONFIG = {"upsample_rates": [5, 4, 2, 2, 2], "upsample_kernel_sizes": [16, 16, 8, 4, 4],
                   "upsample_initial_channel": 1024, "resblock_kernel_sizes": [3, 7, 11],
                   "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]], "num_mels": 64}

@@ -78,6 +78,16 @@ class UNet2DConditionModel:
         hd = [c // h for c, h in zip(cfg["block_out_channels"], _heads(cfg))]
         if any(d != 64 for d in hd):
             raise NotImplementedError(f"attention head width must be 64 (got {hd})")
+        # config fields this implementation does not honour are refused, not ignored (the Tango / Mustango configs
+        # all use the values below; unet_2d_condition.py:130-330; upcast_attention is moot: scores / softmax are fp32)
+        unsupported = {"norm_num_groups": 32, "act_fn": "silu", "class_embed_type": None, "only_cross_attention": False,
+                       "center_input_sample": False, "downsample_padding": 1, "dual_cross_attention": False,
+                       "resnet_time_scale_shift": "default", "time_embedding_type": "positional",
+                       "num_class_embeds": None, "conv_in_kernel": 3, "conv_out_kernel": 3, "mid_block_scale_factor": 1,
+                       "time_cond_proj_dim": None, "timestep_post_act": None, "projection_class_embeddings_input_dim": None}
+        for k, want in unsupported.items():
+            if k in cfg and cfg[k] != want and not (want is False and not cfg[k]):
+                raise NotImplementedError(f"UNet config {k}={cfg[k]!r} is not on the Tango path (supported: {want!r})")
         assert precision in ("bf16", "split")
         self.config = _Cfg(cfg)
         self.precision = precision
@@ -87,9 +97,9 @@ class UNet2DConditionModel:
         self.dtype = torch.float32
         self._sd: Optional[Dict[str, torch.Tensor]] = None
         self._packed = False
+        self.pack_generation = 0     # bumped whenever the packed weights / scratch buffers are rebuilt
         self._bufs: Optional[_Buffers] = None
         self._cond = None
-        self.l2_chunk_mb = float(__import__("os").environ.get("TNG_L2_CHUNK_MB", "0"))  # 0 = off (experiment)
 
     # ----------------------------------------------------------------------------------------- diffusers-style API
     @staticmethod
@@ -234,6 +244,8 @@ class UNet2DConditionModel:
         P["n_extra"] = max((len(t.extra) for t in P["transformers"]), default=0)
         self.P = P
         self._bufs = _Buffers(dev)
+        self._cond = None
+        self.pack_generation += 1
         self._packed = True
 
     # ----------------------------------------------------------------------------------------- building blocks
@@ -326,25 +338,6 @@ class UNet2DConditionModel:
         return out
 
     def _transformer(self, name, t, x, NB, H, W, kv, bias, Lk, shared_half: bool = False):
-        """Transformer2DModel on rows. Large-activation levels are processed in batch chunks whose fp32 hidden state fits
-        comfortably in the 126 MB L2, so that the HBM-bound LayerNorm / K=C linears between the attention kernels find
-        their operands in L2 instead of HBM (the images of a batch are independent)."""
-        R, Cc = NB * H * W, t.C
-        chunk_bytes = self.l2_chunk_mb * 1e6
-        if (not shared_half) and chunk_bytes > 0 and R * Cc * 4 > chunk_bytes and NB % 2 == 0:
-            nchunks = 2
-            while (R // nchunks) * Cc * 4 > chunk_bytes and NB % (2 * nchunks) == 0:
-                nchunks *= 2
-            nb = NB // nchunks
-            out = self._buf(name, (R, Cc), torch.float32)
-            for ci in range(nchunks):
-                r0, r1 = ci * nb * H * W, (ci + 1) * nb * H * W
-                self._transformer_body(name + "_c", t, x[r0:r1], nb, H, W, kv[ci * nb * Lk:(ci + 1) * nb * Lk],
-                                       None if bias is None else bias[ci * nb:(ci + 1) * nb], Lk, out=out[r0:r1])
-            return out
-        return self._transformer_body(name, t, x, NB, H, W, kv, bias, Lk, shared_half=shared_half)
-
-    def _transformer_body(self, name, t, x, NB, H, W, kv, bias, Lk, shared_half: bool = False, out=None):
         """shared_half: `x` holds only the first NB/2 images and stands for both CFG halves (identical latents and
         timestep): everything up to the self-attention output is computed once and duplicated before the
         cross-attention, the first place where the two halves see different data."""
@@ -384,8 +377,7 @@ class UNet2DConditionModel:
         run_linear(t.ff1, n, out_bf16=ff)
         hsb = self._buf("hsb", (R, Cc * s), torch.bfloat16)
         run_linear(t.ff2, ff, res=hs, out_bf16=hsb)
-        if out is None:
-            out = self._buf(name, (R, Cc), torch.float32)
+        out = self._buf(name, (R, Cc), torch.float32)
         run_linear(t.proj_out, hsb, res=x, out_f32=out)
         return out
 

@@ -238,7 +238,33 @@ def spec_sched_step(model_out, cfg, guidance, sample, noise, coef, prev, next_in
             _store_bf16(next_in[r * B * HW:(r + 1) * B * HW], rows, split_off)
 
 
-SPEC = {"softmax_rows": spec_softmax_rows, "transpose_bf16": spec_transpose_bf16, "convt_gather": spec_convt_gather,
+def spec_stft_frames(y, pad, hi, lo):
+    """Reflect padding (no edge repeat) by `pad` on both sides, bf16 hi / lo planes, zero beyond T + 2 pad."""
+    B, T = y.shape
+    z = torch.zeros(B, hi.shape[1])
+    z[:, :T + 2 * pad] = F.pad(y.float().view(B, 1, T), (pad, pad), mode="reflect").view(B, -1)
+    h = z.to(torch.bfloat16)
+    hi.copy_(h)
+    lo.copy_((z - h.float()).to(torch.bfloat16))
+
+
+def spec_stft_magnitude(Fq, bins, mag_op, split_off, log_mag, energy, floor=1e-5):
+    re, im = Fq[:, :bins].float(), Fq[:, bins:2 * bins].float()
+    m = torch.sqrt(re * re + im * im)
+    if mag_op is not None:
+        _store_bf16(mag_op, m, split_off)
+    if log_mag is not None:
+        log_mag.copy_(torch.log(torch.clamp(m, min=floor)))
+    if energy is not None:
+        energy.copy_(torch.norm(m, dim=1))
+
+
+def spec_log_clamp(x, y, floor=1e-5):
+    y.copy_(torch.log(torch.clamp(x.float(), min=floor)))
+
+
+SPEC = {"stft_frames": spec_stft_frames, "stft_magnitude": spec_stft_magnitude, "log_clamp": spec_log_clamp,
+        "softmax_rows": spec_softmax_rows, "transpose_bf16": spec_transpose_bf16, "convt_gather": spec_convt_gather,
         "tanh_to_i16": spec_tanh_to_i16, "sched_step": spec_sched_step, "conv_gemm": spec_conv_gemm, "groupnorm": spec_groupnorm, "layernorm": spec_layernorm, "rmsnorm": spec_rmsnorm,
         "gather_rows": spec_gather_rows, "cast_act": spec_cast_act, "attention": spec_attention,
         "rel_attention": spec_rel_attention, "timestep_embedding": spec_timestep_embedding, "linear_f32": spec_linear_f32}

@@ -221,7 +221,7 @@ def test_cli_main_flow_with_stub_model(tmp_path, monkeypatch):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     res = cli.main(["--test_file", str(man), "--num_steps", "7", "--guidance", "2.5", "--batch_size", "4",
                     "--output_root", str(tmp_path / "o"), "--exp_id", "x", "--latent_h", "32"])
-    assert calls == [([f"prompt {i}" for i in range(5)], 7, 2.5, 4, {"latent_shape": (32, 16)})]
+    assert calls == [([f"prompt {i}" for i in range(5)], 7, 2.5, 4, {"shard": False, "latent_shape": (32, 16)})]
     out = tmp_path / "o" / "x_steps_7_guidance_2.5"
     assert res["output_dir"] == str(out) and sorted(os.listdir(out)) == [f"output_{j}.wav" for j in range(5)]
     assert abs(res["audio_seconds"] - 0.5) < 1e-9 and res["text_encoder"] == "synthetic"

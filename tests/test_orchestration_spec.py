@@ -262,3 +262,38 @@ def test_tango_generate_prompt_to_waveform_vs_oracle(monkeypatch):
                            boolean_prompt_mask=pm1, latents=lat0, latent_shape=(32, 16))
     w1 = opipe.inference(usd, cfg, osched.OracleDDIM(**osched.SD21_CONFIG), pe1, pm1, 3, 1.0, lat0)
     assert rel(l1, w1) < 1e-4
+
+
+def test_tacotron_stft_orchestration_vs_reference_golden():
+    """tango_b200.stft.TacotronSTFT / wav_to_fbank (the overlapping-view basis GEMM, magnitude, mel GEMM, log) against the
+    reference front-end golden (tests/golden/tiny_stft.npz)."""
+    from tango_b200 import stft as pstft
+    gd = np.load(os.path.join(GOLD, "tiny_stft.npz"))
+    FL, HOP, WIN, NMEL, target = (int(v) for v in gd["cfg"])
+    fn = pstft.TacotronSTFT(FL, HOP, WIN, NMEL, 16000, 0, 8000).to(CPU)
+    assert fn.mel_basis.shape == (NMEL, FL // 2 + 1) and fn.mel_basis_source.startswith("slaney")
+    r = fn.load_state_dict({"mel_basis": torch.from_numpy(gd["mel_basis"])}, strict=False)
+    assert "stft_fn.forward_basis" in r.missing_keys and fn.mel_basis_source == "checkpoint"
+    with pytest.raises(RuntimeError):
+        fn.load_state_dict({"mel_basis": torch.zeros(3, 3)}, strict=False)
+    fbank, log_mag, wav = pstft.wav_to_fbank([torch.from_numpy(gd["wave0"]), torch.from_numpy(gd["wave1"])],
+                                             target_length=target, fn_STFT=fn)
+    assert fbank.shape == gd["fbank"].shape and log_mag.shape == gd["log_mag"].shape
+    assert torch.equal(wav, torch.from_numpy(gd["wav"]))
+    e_f, e_l = rel(fbank, gd["fbank"]), rel(log_mag, gd["log_mag"])
+    print(f"TacotronSTFT orchestration: fbank rel {e_f:.3e}, log-mag rel {e_l:.3e}")
+    assert e_f < 1e-4 and e_l < 1e-4
+    with pytest.raises(AssertionError):
+        fn.mel_spectrogram(torch.full((1, 4000), 1.5))
+
+
+def test_slaney_mel_basis_known_properties():
+    """The default mel filter bank (used only when no checkpoint is loaded): triangles on the Slaney scale, area-normalised."""
+    from tango_b200.stft import slaney_mel_basis
+    mb = slaney_mel_basis(16000, 1024, 64, 0, 8000)
+    assert mb.shape == (64, 513) and float(mb.min()) >= 0
+    peaks = mb.argmax(1)
+    assert bool((peaks[1:] > peaks[:-1]).all())                      # centre frequencies increase
+    # below 1 kHz the scale is linear: equal widths, equal heights
+    assert abs(float(mb[2].max() / mb[3].max()) - 1.0) < 0.2
+    assert float(mb[:, 0].sum()) == 0.0 or float(mb[0, 0]) == 0.0   # DC bin carries no weight at fmin = 0

@@ -30,15 +30,25 @@ def _worker(rank, world, port, q):
         sd = {"a.weight": torch.full((3, 4), float(rank + 1)), "b.bias": torch.arange(5, dtype=torch.float32) * (rank + 1)}
         sd = parallel.broadcast_state_dict(sd, src=0)
         ok_bcast = bool((sd["a.weight"] == 1).all() and torch.equal(sd["b.bias"], torch.arange(5, dtype=torch.float32)))
-        # full-batch noise sliced per rank == the rows a single process would use
+        # RNG contract: same seed on every rank, full-batch draw, keep my rows == the rows a single
+        # process would use; per-sample generator lists only consume the local generators
+        from tango_b200.pipeline import AudioDiffusion
         g = torch.Generator().manual_seed(7)
-        full = torch.randn(5, 8, generator=g)
-        part = parallel.shard_rows(full, rank, world)
-        waves = [np.full(4, int(p[1:]), dtype=np.int16) for p in mine]
-        out = parallel.gather_waves(waves, dst=0)
+        part = AudioDiffusion.randn_rows((hi - lo, 8), g, "cpu", rows=(lo, hi, 5))
+        g2 = torch.Generator().manual_seed(7)
+        nxt = AudioDiffusion.randn_rows((hi - lo, 8), g, "cpu", rows=(lo, hi, 5))      # second draw of the stream
+        full = torch.randn(5, 8, generator=g2)
+        full2 = torch.randn(5, 8, generator=g2)
+        ok_rng = torch.equal(part, full[lo:hi]) and torch.equal(nxt, full2[lo:hi])
+        gl = [torch.Generator().manual_seed(100 + i) for i in range(5)]
+        ps = AudioDiffusion.randn_rows((hi - lo, 8), gl, "cpu", rows=(lo, hi, 5))
+        want = torch.cat([torch.randn(1, 8, generator=torch.Generator().manual_seed(100 + i)) for i in range(lo, hi)])
+        ok_rng = ok_rng and torch.equal(ps, want)
+        waves = np.stack([np.full(4, int(p[1:]), dtype=np.int16) for p in mine])
+        out = parallel.allgather_waves(waves)
         mx = parallel.max_over_ranks(float(rank + 1))
         sm = parallel.sum_over_ranks(float(rank + 1))
-        q.put((rank, mine, ok_bcast, part.shape[0], [int(w[0]) for w in out], mx, sm))
+        q.put((rank, mine, ok_bcast, ok_rng, [int(w[0]) for w in out], mx, sm))
     finally:
         dist.destroy_process_group()
 
@@ -67,7 +77,6 @@ def test_world2_gloo():
     (r0, mine0, b0, n0, out0, mx0, sm0), (r1, mine1, b1, n1, out1, mx1, sm1) = res
     assert mine0 == ["p0", "p1", "p2"] and mine1 == ["p3", "p4"]
     assert b0 and b1
-    assert (n0, n1) == (3, 2)
-    assert out0 == [0, 1, 2, 3, 4]          # rank 0 holds every waveform, in prompt order
-    assert out1 == [3, 4]
+    assert n0 and n1
+    assert out0 == out1 == [0, 1, 2, 3, 4]  # every rank holds every waveform, in prompt order
     assert mx0 == mx1 == 2.0 and sm0 == sm1 == 3.0

@@ -1,7 +1,5 @@
 """GPU: AutoencoderKL.encode_first_stage against the reference posterior
-(tests/golden/tiny_vae_encoder.npz). Written after the round's GPU budget was spent: the orchestration is validated on
-the CPU against the C-ABI contract (tests/test_orchestration_spec.py), the kernels by tests/test_kernels_gpu.py; this
-file is their first joint run, hence sorted last."""
+(tests/golden/tiny_vae_encoder.npz); validated on hardware at the end of round 1."""
 import os
 
 import numpy as np
@@ -20,7 +18,6 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-@pytest.mark.xfail(strict=False, reason="not yet run on hardware: written after the round's GPU budget was spent (logic checked on the CPU against the C-ABI contract); XPASS = validated")
 @pytest.mark.parametrize("precision,tol", [("split", 1e-3), ("bf16", 3e-2)])
 def test_vae_encoder_vs_reference_golden(cuda, precision, tol):
     gd = np.load(os.path.join(GOLD, "tiny_vae_encoder.npz"))
