@@ -99,30 +99,28 @@ def synthetic_inputs(B: int, tokens: int, dim: int, rank: int):
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
-def pick_threads():
-    """Host threads for the CPU arm: the fastest of a few counts on a representative 3x3 conv (oversubscribing a
-    128-core box makes torch's CPU kernels several times slower, so 'all cores' is not 'all the threads it can use')."""
-    import torch.nn.functional as F
-    ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
-    x = torch.randn(2, 320, 256, 16)
-    w = torch.randn(320, 320, 3, 3)
-    best, best_t = cands[0], float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
-        F.conv2d(x, w, padding=1)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            F.conv2d(x, w, padding=1)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = c, dt
-    torch.set_num_threads(best)
-    return best
+def host_threads():
+    """Fixed rule for the CPU arm (both the in-line cpu_baseline leg and --impl reference): one thread per PHYSICAL core
+    this process may run on (oversubscribing SMT siblings makes torch's CPU convolutions slower, not faster)."""
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or 0
+    except Exception:
+        phys = 0
+    try:
+        allowed = len(os.sched_getaffinity(0))
+    except Exception:
+        allowed = os.cpu_count() or 1
+    n = min(phys, allowed) if phys else allowed
+    return max(1, n)
 
 
 class CpuReference:
-    """The reference's CPU arithmetic for the path (oracle port, see oracle/__init__.py) on bounded samples."""
+    """The reference's CPU arithmetic for the path (oracle port, see oracle/__init__.py), MEASURED at the c2 batch:
+    one "step" = one denoising step of the benchmark's batch = ONE CFG UNet forward at UNet batch 2 x args.batch
+    (16 x 8 x 256 x 16 latents, 64 tokens), fp32, torch CPU; the decode leg = VAE decoder + HiFi-GAN for the whole
+    batch. Nothing is extrapolated from a smaller batch; only the number of denoising steps (200, identical cost each)
+    is scaled from the measured steps."""
 
     def __init__(self, args):
         from oracle import hifigan as ohifi
@@ -131,74 +129,72 @@ class CpuReference:
         from tango_b200 import synth
         torch.set_grad_enabled(False)
         self.args, self.ounet, self.ovae, self.ohifi, self.synth = args, ounet, ovae, ohifi, synth
-        self.cores = pick_threads()
-        self.cfg = synth.BASE_UNET_CONFIG
+        self.cores = host_threads()
+        torch.set_num_threads(self.cores)
+        self.cfg = synth.BASE_UNET_CONFIG if args.unet == "base" else synth.XL_UNET_CONFIG
         self.usd = synth.synth_state_dict(synth.unet_param_shapes(self.cfg), 0)
         self.vsd = synth.synth_state_dict(synth.vae_decoder_param_shapes(), 0)
-        self.embeds, self.mask = synthetic_inputs(1, args.tokens, self.cfg["cross_attention_dim"], 0)
+        B = args.batch
+        self.embeds, self.mask = synthetic_inputs(B, args.tokens, self.cfg["cross_attention_dim"], 0)
         g = torch.Generator().manual_seed(1234)
-        self.x_full = torch.randn(2, 8, 256, 16, generator=g)
-        self.x_small = self.x_full[:, :, :64].contiguous()
-        # calibration on the quarter-length clip, FLOPs counted live
-        from torch.utils.flop_counter import FlopCounterMode
-        with FlopCounterMode(display=False) as fc:
-            t0 = time.perf_counter()
-            self.fwd(self.x_small, 0)
-            self.t_small = time.perf_counter() - t0
-        self.f_small = float(fc.get_total_flops())
-        self.f_full = 2 * F_UNET          # CFG batch 2
-        self.use_full = self.t_small * self.f_full / self.f_small <= 25.0
-
-    def fwd(self, x, i):
-        return self.ounet.unet_forward(self.usd, self.cfg, x, torch.tensor(995 - 5 * (i % 199)), self.embeds, self.mask)
+        self.lat = torch.randn(B, 8, args.latent_h, 16, generator=g)
 
     def step_seconds(self, i):
-        """Seconds of one CFG UNet forward for one prompt at 256x16 (measured, or FLOP-scaled from the 64x16 sample)."""
-        x = self.x_full if self.use_full else self.x_small
+        """One denoising step at the benchmark batch: the CFG-doubled UNet forward (models.py:235-243)."""
+        x = torch.cat([self.lat] * 2)
         t0 = time.perf_counter()
-        self.fwd(x, i)
-        dt = time.perf_counter() - t0
-        return dt if self.use_full else dt * self.f_full / self.f_small
+        self.ounet.unet_forward(self.usd, self.cfg, x, torch.tensor(995 - 5 * (i % 199)), self.embeds, self.mask)
+        return time.perf_counter() - t0
 
-    def decode_seconds(self):
-        """VAE decoder + HiFi-GAN for one sample; a quarter-length latent scaled by 4 when the box is slow."""
-        z = self.x_full[:1] if self.use_full else self.x_small[:1]
+    def decode_seconds(self, n=None):
+        """decode_first_stage + decode_to_waveform for n samples of the batch (default: all of it), one at a time as
+        a memory-bounded CPU run would; returns seconds for the WHOLE batch (n < batch is scaled by batch / n)."""
+        B = self.args.batch
+        n = B if n is None else max(1, min(n, B))
         t0 = time.perf_counter()
-        mel = self.ovae.decode_first_stage(self.vsd, z, self.synth.VAE_CONFIG["scale_factor"])
-        self.ohifi.decode_to_waveform(self.vsd, mel)
-        dt = time.perf_counter() - t0
-        return dt if self.use_full else dt * 4.0
+        for k in range(n):
+            mel = self.ovae.decode_first_stage(self.vsd, self.lat[k:k + 1], self.synth.VAE_CONFIG["scale_factor"])
+            self.ohifi.decode_to_waveform(self.vsd, mel)
+        return (time.perf_counter() - t0) * B / n
 
-    def describe(self, t_fwd, t_dec):
+    def describe(self, t_step, n_steps, t_dec, n_dec):
         a = self.args
-        what = ("1 UNet forward at CFG batch 2 (1 prompt, 64 tokens, 256x16 latent)" if self.use_full else
-                f"1 UNet forward at CFG batch 2 on a quarter-length latent (64x16, {self.f_small / 1e9:.0f} GFLOP counted live) "
-                f"scaled by the FLOP ratio to the 256x16 forward ({self.f_full / 1e9:.0f} GFLOP)")
-        return (f"oracle port, torch CPU fp32, {self.cores} threads: per step {what} = {t_fwd:.2f} s; VAE+HiFi-GAN for 1 sample "
-                f"= {t_dec:.2f} s (timed once); extrapolated linearly to {a.denoise_steps} denoising steps and batch {a.batch}")
+        return (f"oracle port, torch CPU fp32, {self.cores} threads (= physical cores): {n_steps} measured denoising step(s) at "
+                f"the benchmark batch (UNet batch {2 * a.batch}, {a.latent_h}x16 latents, {a.tokens} tokens) = {t_step:.2f} s "
+                f"each; VAE+HiFi-GAN measured on {n_dec} of {a.batch} samples = {t_dec:.2f} s per batch; "
+                f"pass = {a.denoise_steps} x step + decode")
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's CPU arithmetic for this path on the box's host cores (rank 0 only)."""
+    """`--impl reference`: the reference's CPU arithmetic for this path on the box's host cores (rank 0 only). The
+    requested K timed steps are capped so that the run ends within a few minutes (each step costs tens of seconds at the
+    c2 batch): `steps_timed` says how many were actually timed; warm-up is one step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    t_start = time.perf_counter()
     ref = CpuReference(args)
-    t_dec = ref.decode_seconds()
+    ref.step_seconds(0)                                    # warm-up (allocator, thread pool)
     times = []
-    for i in range(args.warmup + args.steps):
-        dt = ref.step_seconds(i)
-        if i >= args.warmup:
-            times.append(dt)
-    t_fwd = float(np.mean(times))
-    per_sample = args.denoise_steps * t_fwd + t_dec       # one prompt = one CFG forward per denoising step
-    value = AUDIO_S_PER_SAMPLE / per_sample
+    budget_s = args.reference_budget_s
+    while len(times) < max(1, args.steps):
+        times.append(ref.step_seconds(len(times) + 1))
+        if len(times) >= 2 and time.perf_counter() - t_start + times[-1] > budget_s:
+            break
+    t_step = float(np.mean(times))
+    n_dec = args.batch if t_step * 0.6 * args.batch < 60 else 2
+    t_dec = ref.decode_seconds(n_dec)
+    per_pass = args.denoise_steps * t_step + t_dec
+    audio_s = (4 * args.latent_h * 160 + 32) / 16000.0
+    value = args.batch * audio_s / per_pass
     line = {"impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_sample * args.batch * 1e3,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "steps_timed": len(times), "warmup_timed": 1,
+            "ms_per_step": per_pass * 1e3, "timed_region_s": float(np.sum(times)) + t_dec * n_dec / args.batch,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, 1),
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": ref.cores, "kind": "port",
-                             "sample": ref.describe(t_fwd, t_dec)},
+                             "sample": ref.describe(t_step, len(times), t_dec, n_dec),
+                             "step_s": times, "decode_s_per_batch": t_dec},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -247,13 +243,20 @@ def run_ours(args):
     prompts = [f"synthetic prompt {rank}-{i}" for i in range(B)]
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
 
+    decode_ms = []
+
     def one_pass_device():
         lat = t.model.inference(prompts, t.scheduler, args.denoise_steps, args.guidance, prompt_embeds=embeds_d,
                                 boolean_prompt_mask=mask_d, generator=gen, latent_shape=latent_shape)
         B_, Cl, H, W = lat.shape
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
         rows = lat.permute(0, 2, 3, 1).reshape(B_ * H * W, Cl).contiguous()
         mel = t.vae.decode_rows(rows, B_, H, W)
-        return t.vae.vocoder_rows(mel.view(B_ * 4 * H, 4 * W), B_, 4 * H)
+        out = t.vae.vocoder_rows(mel.view(B_ * 4 * H, 4 * W), B_, 4 * H)
+        d1.record()
+        decode_ms.append((d0, d1))
+        return out
 
     def one_pass_e2e():
         return t.generate_for_batch(prompts, steps=args.denoise_steps, guidance=args.guidance, batch_size=B,
@@ -288,6 +291,7 @@ def run_ours(args):
     dev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
     launches = (L.launch_count() - n0) + graph_launches
+    dec_ms = float(np.mean([a.elapsed_time(b) for a, b in decode_ms[-args.steps:]]))
     dev_ms = parallel.max_over_ranks(dev_ms, dev)
     value = world * B * audio_s * args.steps / (dev_ms / 1e3)
 
@@ -302,6 +306,11 @@ def run_ours(args):
     e2e_value = world * B * audio_s * args.steps / e2e_s
     h2d = embeds_pin.numel() * 4 + mask_pin.numel()
     d2h = sum(int(w.nbytes) for w in waves)
+
+    # ---------------- BASELINE.json configs[3] / configs[4] at 8 GPUs (every rank takes part; rank 0 reports)
+    extra = None
+    if world == 8 and not args.no_extra_configs and args.unet == "base" and args.latent_h == 256:
+        extra = extra_configs(args, dev, rank, world, barrier, t)
 
     if rank != 0:
         if world > 1:
@@ -326,10 +335,12 @@ def run_ours(args):
     gm = prof.get("gemm_tc", {"launches": 1, "ms": 1.0, "flops": 0.0})
     at = prof.get("attention_tc", {"launches": 1, "ms": 1.0, "flops": 0.0})
     achieved = gm["flops"] / (gm["ms"] / 1e3) / 1e12
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    traffic = None      # dram bytes per launch of the dominant kernel: only ncu can measure it (profiles/, per round)
+    for tp in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", tp)
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            break
     roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv/linear)",
             "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
@@ -346,6 +357,26 @@ def run_ours(args):
     whole = f_total * args.steps / (dev_ms / 1e3) / 1e12
     roof["whole_path_tflops"] = whole
     roof["whole_path_frac"] = whole / pk["bf16_tflops_sustained"]
+    # every kernel family of the instrumented forwards (2 denoising steps): share of the step, achieved rate against the
+    # roofline that bounds it (tensor families: algorithmic TFLOP/s; HBM families: algorithmic GB/s)
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    fam = {}
+    for name, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        e = {"launches_per_step": v["launches"] / 2, "ms_per_step": v["ms"] / 2, "share": v["ms"] / tot_ms}
+        if v["flops"] > 0:
+            e["tflops"] = v["flops"] / (v["ms"] / 1e3) / 1e12
+            e["frac_of_bf16_sustained"] = e["tflops"] / pk["bf16_tflops_sustained"]
+        elif v["bytes"] > 0:
+            e["gbs"] = v["bytes"] / (v["ms"] / 1e3) / 1e9
+            e["frac_of_hbm"] = e["gbs"] / pk["hbm_gbs"]
+        fam[name] = e
+    roof["kernel_families"] = fam
+
+    # ---------------- the mode that meets the north star's 1e-3 (precision="split"): its throughput on the same config,
+    # and how far the timed bf16 mode drifts from it over the full 200-step chain on identical noise
+    parity = None
+    if world == 1 and not args.no_parity_mode and args.precision == "bf16":
+        parity = parity_mode_leg(args, t, cfg, dev, prompts, embeds_d, mask_d, latent_shape, audio_s)
 
     # ---------------- text-conditioning front-end: reported beside the metric, not inside it
     # (BASELINE.json's metric excludes text encoding). FLAN-T5 encoder of the UNet's width, seeded random weights,
@@ -365,7 +396,12 @@ def run_ours(args):
             "data": "synthetic (seeded random weights of the Tango base architecture, random 64-token conditioning)",
             "config": workload_config(args, world), "unet_step_ms": float(np.mean(unet_ms)),
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "decode_ms": {"value": dec_ms, "what": f"VAE decoder + HiFi-GAN for {B} samples, eager launches, inside the timed pass"}}
+    if parity is not None:
+        line["parity_mode"] = parity
+    if extra is not None:
+        line["configs"] = extra
     if text is not None:
         line["text_encoder"] = text
     if cpu is not None:
@@ -373,6 +409,98 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_mode_leg(args, t_bf16, cfg, dev, prompts, embeds_d, mask_d, latent_shape, audio_s):
+    from tango_b200.pipeline import Tango
+    ts = Tango.from_synthetic(unet_config=cfg, device=dev, precision="split", scheduler=args.scheduler)
+
+    def run(t, steps, seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        lat = t.model.inference(prompts, t.scheduler, steps, args.guidance, prompt_embeds=embeds_d,
+                                boolean_prompt_mask=mask_d, generator=g, latent_shape=latent_shape)
+        B_, Cl, H, W = lat.shape
+        rows = lat.permute(0, 2, 3, 1).reshape(B_ * H * W, Cl).contiguous()
+        mel = t.vae.decode_rows(rows, B_, H, W)
+        wf, wi = t.vae.vocoder_rows(mel.view(B_ * 4 * H, 4 * W), B_, 4 * H)
+        return lat.clone(), mel.clone(), wf.clone()
+
+    run(ts, 3, 1)                                          # capture + warm-up at the same shapes
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lat_s, mel_s, wav_s = run(ts, args.denoise_steps, 4321)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    lat_b, mel_b, wav_b = run(t_bf16, args.denoise_steps, 4321)
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm())
+
+    # short chain for scale: the same comparison after 10 steps
+    lat_s10, _, _ = run(ts, 10, 99)
+    lat_b10, _, _ = run(t_bf16, 10, 99)
+    out = {"precision": "split (bf16 hi/lo 3-term products on the tensor cores; GPU parity tests hold it to <= 1e-3 of the "
+                        "fp32 reference: tests/test_config1_gpu.py)",
+           "value": args.batch * audio_s / (ms / 1e3), "unit": "audio-s/s", "passes_timed": 1, "ms_per_pass": ms,
+           "unet_step_ms": ts.model.last_step_ms,
+           "bf16_vs_split": {"what": f"relative L2 distance of the timed bf16 mode from the split mode, same seed / noise, "
+                                     f"{args.scheduler.upper()} chain",
+                             "latents_after_10_steps": rel(lat_b10, lat_s10),
+                             f"latents_after_{args.denoise_steps}_steps": rel(lat_b, lat_s),
+                             "mel": rel(mel_b, mel_s), "waveform": rel(wav_b, wav_s)}}
+    del ts
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_configs(args, dev, rank, world, barrier, t_base):
+    """BASELINE.json configs[3] (XL UNet, batch 32, 100 steps, 4 prompts per GPU) and configs[4] (base UNet, batch 64,
+    200 steps, 30 s clips = 768 x 16 latents, 8 prompts per GPU) on the 8 GPUs: 2 timed passes each after one warm-up,
+    device-timed, max over ranks, whole-job audio-s/s."""
+    from tango_b200 import parallel, synth
+    from tango_b200.pipeline import Tango
+    out = {}
+    specs = [("c4", "xl", 32, 100, 256), ("c5", "base", 64, 200, 768)]
+    for name, unet, gbatch, steps, lh in specs:
+        B = gbatch // world
+        cfg = synth.BASE_UNET_CONFIG if unet == "base" else synth.XL_UNET_CONFIG
+        t = t_base if unet == "base" else Tango.from_synthetic(unet_config=cfg, device=dev, precision=args.precision,
+                                                               scheduler=args.scheduler)
+        emb, msk = synthetic_inputs(B, args.tokens, cfg["cross_attention_dim"], 100 + rank)
+        emb, msk = emb.to(dev), msk.to(dev)
+        gen = torch.Generator(device=dev).manual_seed(99 + rank)
+        prompts = [f"{name} prompt {rank}-{i}" for i in range(B)]
+        audio_s = (4 * lh * 160 + 32) / 16000.0
+
+        def one():
+            lat = t.model.inference(prompts, t.scheduler, steps, args.guidance, prompt_embeds=emb, boolean_prompt_mask=msk,
+                                    generator=gen, latent_shape=(lh, 16))
+            B_, Cl, H, W = lat.shape
+            rows = lat.permute(0, 2, 3, 1).reshape(B_ * H * W, Cl).contiguous()
+            mel = t.vae.decode_rows(rows, B_, H, W)
+            return t.vae.vocoder_rows(mel.view(B_ * 4 * H, 4 * W), B_, 4 * H)
+
+        one()
+        barrier()
+        passes = 2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(passes):
+            one()
+        e1.record()
+        barrier()
+        ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+        out[name] = {"workload": f"Tango {unet} UNet, batch {gbatch} sharded {B}/GPU over {world} GPUs, {steps} "
+                                 f"{args.scheduler.upper()} steps, CFG {args.guidance}, {audio_s:.2f} s clips, {args.precision}",
+                     "value": gbatch * audio_s * passes / (ms / 1e3), "unit": "audio-s/s", "passes_timed": passes,
+                     "ms_per_pass": ms / passes, "unet_step_ms": t.model.last_step_ms}
+        if unet != "base":
+            del t
+            torch.cuda.empty_cache()
+    return out
 
 
 def text_encoder_leg(args, dev):
@@ -405,11 +533,14 @@ def text_encoder_leg(args, dev):
 
 
 def cpu_baseline(args):
+    """In-line CPU leg (N = 1): ONE measured denoising step at the benchmark batch + the decode of 2 of its samples
+    (~30-60 s of CPU work on the box's physical cores) — same procedure and thread rule as --impl reference."""
     ref = CpuReference(args)
-    t_fwd = ref.step_seconds(0)
-    t_dec = ref.decode_seconds()
-    v = AUDIO_S_PER_SAMPLE / (args.denoise_steps * t_fwd + t_dec)
-    return {"value": v, "unit": "audio-s/s", "cores": ref.cores, "kind": "port", "sample": ref.describe(t_fwd, t_dec)}
+    t_step = ref.step_seconds(0)
+    t_dec = ref.decode_seconds(2)
+    audio_s = (4 * args.latent_h * 160 + 32) / 16000.0
+    v = args.batch * audio_s / (args.denoise_steps * t_step + t_dec)
+    return {"value": v, "unit": "audio-s/s", "cores": ref.cores, "kind": "port", "sample": ref.describe(t_step, 1, t_dec, 2)}
 
 
 def main():
@@ -428,7 +559,14 @@ def main():
     ap.add_argument("--no-text-encoder", action="store_true", help="skip the FLAN-T5 front-end timing leg")
     ap.add_argument("--latent-h", type=int, default=256, help="latent time frames: 256 = 10.24 s (reference), 768 = 30.7 s")
     ap.add_argument("--unet", default="base", choices=["base", "xl"])
+    ap.add_argument("--reference-budget-s", type=float, default=150.0,
+                    help="--impl reference: stop timing further steps once this much wall time has been used")
+    ap.add_argument("--no-parity-mode", action="store_true", help="skip the split-precision (1e-3 mode) leg")
+    ap.add_argument("--no-extra-configs", action="store_true", help="at --gpus 8: skip the c4 / c5 legs")
     args = ap.parse_args()
+    knobs = sorted(k for k in os.environ if k.startswith("TNG_"))
+    if knobs:
+        raise SystemExit(f"bench.py: refusing to run with experiment knobs set in the environment: {knobs}")
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -275,6 +275,23 @@ class AudioDiffusion:
         full = torch.randn((total,) + tuple(shape[1:]), generator=generator, device=gdev, dtype=dtype).to(device)
         return full if (lo == 0 and hi == total) else full[lo:hi].contiguous()
 
+    def advance_rng(self, total_batch, inference_scheduler, num_steps, generator=None, latent_shape=LATENT_HW):
+        """Consume exactly the random numbers `inference` would for a `total_batch`-sample batch without running it:
+        a rank whose shard of a chunk is empty calls this so that its (shared-seed) stream stays aligned with the
+        one-GPU run for the chunks that follow. Per-sample generator lists need nothing."""
+        if isinstance(generator, (list, tuple)) and len(generator) > 1:
+            return
+        if isinstance(generator, (list, tuple)):
+            generator = generator[0]
+        sch = inference_scheduler
+        sch.set_timesteps(num_steps, device=self.device)
+        gdev = self.device if generator is None else generator.device
+        shape = (total_batch, self.unet.config["in_channels"], *latent_shape)
+        torch.randn(shape, generator=generator, device=gdev, dtype=torch.float32)
+        for i in range(len(sch.timesteps)):
+            if sch._needs_noise(sch.timestep_at(i)):
+                torch.randn(shape, generator=generator, device=gdev, dtype=torch.float32)
+
     def prepare_latents(self, batch_size, inference_scheduler, num_channels_latents, dtype, device, generator=None,
                         latent_shape=LATENT_HW, rows=None):
         """models.py:259-264."""
@@ -509,6 +526,9 @@ class Tango:
                     latents = self.model.inference(batch[lo:hi], self.scheduler, steps, guidance, samples,
                                                    disable_progress=disable_progress, generator=g, noise_rows=rows, **kw)
                     wave = self._decode(latents)
+            elif kw.get("latents") is None and kw.get("noises") is None:
+                self.model.advance_rng(len(batch) * samples, self.scheduler, steps, g,
+                                       kw.get("latent_shape", LATENT_HW))
             if world > 1:
                 wave = parallel.allgather_waves(wave, self.device)
             outputs += [item for item in wave]
