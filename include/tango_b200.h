@@ -97,6 +97,13 @@ typedef struct {
   float act_param;
   int32_t split_off;   /* 0 = off */
   int32_t block_n;     /* N tile: 0 = auto; one of 32, 64, 128, 160, 256 */
+  /* GroupNorm statistics of the fp32 output for the norm that consumes it (resnet.py:555,581; transformer_2d.py:253):
+   * gn_stats[(img * Ncols + n) * 2 + {0, 1}] += sum / sum of squares of out_f32[:, n] over the stats_hw rows of image
+   * img = row / stats_hw (fp64 accumulators the caller zeroes; per CHANNEL, so that any grouping - also across the
+   * channel concat of a skip connection - is a sum of entries). Emitted from the epilogue of the producing GEMM when
+   * every tile is full, otherwise by a pass over the output that follows it in the stream. NULL = off. */
+  double* gn_stats;
+  int64_t stats_hw;
 } tng_gemm_desc;
 
 int tng_conv_gemm(const tng_gemm_desc* d, void* stream);
@@ -130,14 +137,18 @@ int tng_attention(const tng_attn_desc* d, void* stream);
  * Replaces: nn.GroupNorm + SiLU in ResnetBlock2D (resnet.py:555-557,581-587), conv_norm_out
  *           (unet_2d_condition.py:699-701), Transformer2DModel.norm (transformer_2d.py:253),
  *           torch.cat skip (unet_2d_blocks.py:2210,2495), VAE Normalize+swish (modules.py:37-41,155-175).
- * stats: fp64 [NB, groups, 2] (sum, sumsq) — zeroed by tng_groupnorm_stats before accumulation.
+ * Statistics are kept PER CHANNEL: col_stats fp64 [NB, C, 2] (sum, sum of squares over the HW pixels of an image). They
+ * normally come out of the producing tng_conv_gemm (gn_stats above); tng_groupnorm_stats is the stand-alone pass for
+ * tensors no GEMM produced (it ADDS to col_stats: the caller zeroes them).
  */
-int tng_groupnorm_stats(const void* x0, int32_t dt0, int64_t C0, const void* x1, int32_t dt1, int64_t C1,
-                        int64_t NB, int64_t HW, int32_t groups, double* stats, void* stream);
-/* y = act((x - mean) * rstd * gamma + beta) -> bf16 [NB*HW, ld_y] (+ lo half at split_off if > 0);
- * optional fp32 copy of the *raw* concat input to raw_out (used as the shortcut operand). */
-int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, const void* x1, int32_t dt1, int64_t C1,
-                        int64_t NB, int64_t HW, int32_t groups, const double* stats, const float* gamma,
+int tng_groupnorm_stats(const void* x, int32_t dt, int64_t C, int64_t ld, int64_t NB, int64_t HW, double* col_stats,
+                        void* stream);
+/* y = act((x - mean) * rstd * gamma + beta) -> bf16 [NB*HW, ld_y] (+ lo half at split_off if > 0) for x = [x0 | x1]
+ * (x1 / stats1 may be NULL); mean / rstd of group g over its (C0 + C1) / groups consecutive channels of the concat, from
+ * stats0 [NB, C0, 2] and stats1 [NB, C1, 2]; optional bf16 copy of the *raw* concat input to raw_bf16 (the operand of
+ * the fused 1x1 shortcut conv). */
+int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, const double* stats0, const void* x1, int32_t dt1,
+                        int64_t C1, const double* stats1, int64_t NB, int64_t HW, int32_t groups, const float* gamma,
                         const float* beta, float eps, int32_t act, void* y, int64_t ld_y, int32_t split_off,
                         void* raw_bf16, int64_t ld_raw, int32_t raw_split_off, void* stream);
 

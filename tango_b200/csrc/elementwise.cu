@@ -71,50 +71,29 @@ __device__ __forceinline__ void gn_accum(const void* base, long long idx0, long 
   }
 }
 
-__global__ void __launch_bounds__(256) gn_stats_kernel(const void* x0, int dt0, int C0, const void* x1, int dt1, int C1,
-                                                        long long HW, int groups, double* stats, int GN_ROWS) {
-  __shared__ float s_sum[64], s_sq[64];
+// Per-(image, channel) sums and sums of squares (fp32 partials over this CTA's rows, fp64 atomics across CTAs).
+__global__ void __launch_bounds__(256) col_stats_kernel(const void* x, int dt, int C, long long ld, long long HW,
+                                                         double* stats, int GN_ROWS) {
   const int n = blockIdx.y;
   const long long r0 = static_cast<long long>(blockIdx.x) * GN_ROWS;
-  const int C = C0 + C1;
-  const int cpg = C / groups;
   const int Q = C / 4;
   const int QT = Q < 256 ? Q : 256;
   const int RL = 256 / QT;
   const int rl = threadIdx.x / QT;
-  if (threadIdx.x < groups) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-  __syncthreads();
+  if (rl >= RL) return;
   const int nrows = static_cast<int>((HW - r0) < GN_ROWS ? (HW - r0) : GN_ROWS);
-  if (rl < RL) {
-    for (int q = threadIdx.x - rl * QT; q < Q; q += QT) {
-      const int c = q * 4;
-      const bool first = c < C0;
-      const void* base = first ? x0 : x1;
-      const int dt = first ? dt0 : dt1;
-      const int Cs = first ? C0 : C1;
-      const int cc = first ? c : c - C0;
-      float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-      const long long idx0 = (n * HW + r0) * Cs + cc;
-      if (dt == TNG_DT_F32) gn_accum<false>(base, idx0, Cs, rl, nrows, RL, s, ss);
-      else gn_accum<true>(base, idx0, Cs, rl, nrows, RL, s, ss);
-      const int g0 = c / cpg, g3 = (c + 3) / cpg;
-      if (g0 == g3) {
-        atomicAdd(&s_sum[g0], (s[0] + s[1]) + (s[2] + s[3]));
-        atomicAdd(&s_sq[g0], (ss[0] + ss[1]) + (ss[2] + ss[3]));
-      } else {
+  for (int q = threadIdx.x - rl * QT; q < Q; q += QT) {
+    const int c = q * 4;
+    float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    const long long idx0 = (n * HW + r0) * ld + c;
+    if (dt == TNG_DT_F32) gn_accum<false>(x, idx0, ld, rl, nrows, RL, s, ss);
+    else gn_accum<true>(x, idx0, ld, rl, nrows, RL, s, ss);
+    double* sp = stats + (static_cast<long long>(n) * C + c) * 2;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int g = (c + j) / cpg;
-          atomicAdd(&s_sum[g], s[j]);
-          atomicAdd(&s_sq[g], ss[j]);
-        }
-      }
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(sp + 2 * j, static_cast<double>(s[j]));
+      atomicAdd(sp + 2 * j + 1, static_cast<double>(ss[j]));
     }
-  }
-  __syncthreads();
-  if (threadIdx.x < groups) {
-    atomicAdd(&stats[(static_cast<long long>(n) * groups + threadIdx.x) * 2 + 0], static_cast<double>(s_sum[threadIdx.x]));
-    atomicAdd(&stats[(static_cast<long long>(n) * groups + threadIdx.x) * 2 + 1], static_cast<double>(s_sq[threadIdx.x]));
   }
 }
 
@@ -145,8 +124,9 @@ __device__ __forceinline__ void gn_apply_rows(const void* base, long long idx0, 
 }
 
 template <bool SILU, bool SPLIT, bool RAW>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, int C0, const void* x1, int dt1, int C1,
-                                                        long long HW, int groups, const double* stats,
+__global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, int C0, const double* stats0,
+                                                        const void* x1, int dt1, int C1, const double* stats1,
+                                                        long long HW, int groups, int tpg,
                                                         const float* gamma, const float* beta, float eps,
                                                         __nv_bfloat16* y, long long ld_y, int split_off,
                                                         __nv_bfloat16* raw, long long ld_raw, int raw_split_off, int GN_ROWS) {
@@ -154,15 +134,31 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, 
   const int n = blockIdx.y;
   const int C = C0 + C1;
   const int cpg = C / groups;
-  if (threadIdx.x < groups) {
-    const double cnt = static_cast<double>(HW) * cpg;
-    const double sum = stats[(static_cast<long long>(n) * groups + threadIdx.x) * 2 + 0];
-    const double sq = stats[(static_cast<long long>(n) * groups + threadIdx.x) * 2 + 1];
-    const double mean = sum / cnt;
-    double var = sq / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = static_cast<float>(mean);
-    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  {
+    // group statistics from the per-channel accumulators of the two sources: tpg threads (a power of two <= 32, lanes of
+    // one warp) share a group
+    const int g = threadIdx.x / tpg, sub = threadIdx.x % tpg;
+    double sum = 0.0, sq = 0.0;
+    if (g < groups) {
+      for (int c = g * cpg + sub; c < (g + 1) * cpg; c += tpg) {
+        const double* sp = (c < C0) ? stats0 + (static_cast<long long>(n) * C0 + c) * 2
+                                    : stats1 + (static_cast<long long>(n) * C1 + (c - C0)) * 2;
+        sum += sp[0];
+        sq += sp[1];
+      }
+    }
+    for (int o = tpg >> 1; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (g < groups && sub == 0) {
+      const double cnt = static_cast<double>(HW) * cpg;
+      const double mean = sum / cnt;
+      double var = sq / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = static_cast<float>(mean);
+      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
   }
   __syncthreads();
   const long long r0 = static_cast<long long>(blockIdx.x) * GN_ROWS;
@@ -627,35 +623,43 @@ static inline int grid_for(long long total, int block = 256) {
 using namespace tng;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
-extern "C" int tng_groupnorm_stats(const void* x0, int32_t dt0, int64_t C0, const void* x1, int32_t dt1, int64_t C1,
-                                   int64_t NB, int64_t HW, int32_t groups, double* stats, void* stream) {
-  const int64_t C = C0 + (x1 ? C1 : 0);
-  if (!x0 || !stats || groups <= 0 || groups > 64 || C % groups || C0 % 4 || (x1 && C1 % 4))
-    return set_error(TNG_EINVAL, "groupnorm_stats: bad shape C0=%lld C1=%lld groups=%d", (long long)C0, (long long)C1, groups);
-  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * NB * groups, ST(stream));
-  if (e != cudaSuccess) return set_error(TNG_ECUDA, "memset: %s", cudaGetErrorString(e));
+namespace tng {
+int launch_col_stats(const void* x, int dt, long long C, long long ld, long long NB, long long HW, double* col_stats,
+                     cudaStream_t st) {
+  if (!x || !col_stats || C <= 0 || C % 4 || ld % 4 || NB <= 0 || HW <= 0 || (reinterpret_cast<uintptr_t>(x) & 15))
+    return set_error(TNG_EINVAL, "groupnorm_stats: bad shape C=%lld ld=%lld", C, ld);
   const int gn_rows = gn_rows_for(NB, HW);
   dim3 grid((unsigned)((HW + gn_rows - 1) / gn_rows), (unsigned)NB);
-  gn_stats_kernel<<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, x1, dt1, x1 ? (int)C1 : 0, HW, groups, stats, gn_rows);
+  col_stats_kernel<<<grid, 256, 0, st>>>(x, dt, (int)C, ld, HW, col_stats, gn_rows);
   count_launch();
-  return check_launch("gn_stats");
+  return check_launch("col_stats");
+}
+}  // namespace tng
+
+extern "C" int tng_groupnorm_stats(const void* x, int32_t dt, int64_t C, int64_t ld, int64_t NB, int64_t HW,
+                                   double* col_stats, void* stream) {
+  return launch_col_stats(x, dt, C, ld, NB, HW, col_stats, ST(stream));
 }
 
-extern "C" int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, const void* x1, int32_t dt1, int64_t C1,
-                                   int64_t NB, int64_t HW, int32_t groups, const double* stats, const float* gamma,
-                                   const float* beta, float eps, int32_t act, void* y, int64_t ld_y, int32_t split_off,
-                                   void* raw_bf16, int64_t ld_raw, int32_t raw_split_off, void* stream) {
+extern "C" int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, const double* stats0, const void* x1,
+                                   int32_t dt1, int64_t C1, const double* stats1, int64_t NB, int64_t HW, int32_t groups,
+                                   const float* gamma, const float* beta, float eps, int32_t act, void* y, int64_t ld_y,
+                                   int32_t split_off, void* raw_bf16, int64_t ld_raw, int32_t raw_split_off, void* stream) {
   const int64_t C = C0 + (x1 ? C1 : 0);
-  if (!x0 || !stats || !y || C % groups || C0 % 4 || (x1 && C1 % 4) || ld_y % 4 || split_off % 4 || C > 8192)
+  if (!x0 || !stats0 || (x1 && !stats1) || !y || groups <= 0 || groups > 64 || C % groups || C0 % 4 || (x1 && C1 % 4) ||
+      ld_y % 4 || split_off % 4 || C > 8192)
     return set_error(TNG_EINVAL, "groupnorm_apply: bad shape");
   const int gn_rows = gn_rows_for(NB, HW);
   dim3 grid((unsigned)((HW + gn_rows - 1) / gn_rows), (unsigned)NB);
   if (act != TNG_ACT_NONE && act != TNG_ACT_SILU) return set_error(TNG_EINVAL, "groupnorm_apply: act must be NONE or SILU");
+  int tpg = 1;
+  while (tpg * 2 * groups <= 256 && tpg < 32) tpg *= 2;
   const bool silu = act == TNG_ACT_SILU, split = split_off > 0, hasraw = raw_bf16 != nullptr;
-#define TNG_GN_LAUNCH(S, P, R)                                                                                          \
-  gn_apply_kernel<S, P, R><<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, x1, dt1, x1 ? (int)C1 : 0, HW, groups, stats, \
-                                                          gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y,   \
-                                                          split_off, reinterpret_cast<__nv_bfloat16*>(raw_bf16), ld_raw, \
+#define TNG_GN_LAUNCH(S, P, R)                                                                                           \
+  gn_apply_kernel<S, P, R><<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, stats0, x1, dt1, x1 ? (int)C1 : 0, stats1, HW, \
+                                                          groups, tpg, gamma, beta, eps,                                  \
+                                                          reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off,           \
+                                                          reinterpret_cast<__nv_bfloat16*>(raw_bf16), ld_raw,             \
                                                           raw_split_off, gn_rows)
   if (silu) {
     if (split) { if (hasraw) TNG_GN_LAUNCH(true, true, true); else TNG_GN_LAUNCH(true, true, false); }

@@ -57,6 +57,10 @@ struct GemmKernelParams {
   int split_off;
   int vec_ok;    // all row strides / bases allow 16-byte vector access
   int fast_epi;  // vec_ok && Ncols % 4 == 0
+  // GroupNorm statistics of the fp32 output, emitted from the epilogue (full-tile launches only, see the host side):
+  // col_stats[(img * Ncols + col) * 2 + {0, 1}] += sum / sum of squares over the rows of image img = row / stats_hw
+  double* col_stats;
+  long long stats_hw;
 };
 
 // PAIR: cta_group::2 — each CTA of the pair stages its own 128 A rows and only HALF of the weight tile
@@ -219,7 +223,7 @@ __device__ __forceinline__ void epi_chunk(const GemmKernelParams& p, const float
 // pointer advances by a constant stride — a few instructions per 16-byte access, no per-element predicates.
 template <bool RES, bool F32, bool BF16>
 __device__ __forceinline__ void epi_chunk_full(const GemmKernelParams& p, const float* st, long long r0, int img0,
-                                               int rsub, int cg, int col, bool rv_uniform) {
+                                               int rsub, int cg, int col, bool rv_uniform, long long stats_img) {
   float4 add4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.bias) add4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
   if (p.rowvec && rv_uniform) {
@@ -282,6 +286,32 @@ __device__ __forceinline__ void epi_chunk_full(const GemmKernelParams& p, const 
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(op + i * os) = a[i];
+    if (p.col_stats) {
+      // Column sums of this warp's 32 rows x 32 columns (all rows belong to image stats_img): 8 rows in registers,
+      // then across the four row-lanes (lane bits 3 and 4); lanes 0..7 hold the totals of their 4 columns and add
+      // them to the fp64 per-(image, channel) accumulators — fp32 partials over 32 values, fp64 across tiles.
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s0 += a[i].x; s1 += a[i].y; s2 += a[i].z; s3 += a[i].w;
+        q0 = fmaf(a[i].x, a[i].x, q0); q1 = fmaf(a[i].y, a[i].y, q1);
+        q2 = fmaf(a[i].z, a[i].z, q2); q3 = fmaf(a[i].w, a[i].w, q3);
+      }
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+        q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+        q2 += __shfl_xor_sync(0xffffffffu, q2, o); q3 += __shfl_xor_sync(0xffffffffu, q3, o);
+      }
+      if (rsub == 0) {
+        double* sp = p.col_stats + (stats_img * p.Ncols + col) * 2;
+        atomicAdd(sp + 0, static_cast<double>(s0)); atomicAdd(sp + 1, static_cast<double>(q0));
+        atomicAdd(sp + 2, static_cast<double>(s1)); atomicAdd(sp + 3, static_cast<double>(q1));
+        atomicAdd(sp + 4, static_cast<double>(s2)); atomicAdd(sp + 5, static_cast<double>(q2));
+        atomicAdd(sp + 6, static_cast<double>(s3)); atomicAdd(sp + 7, static_cast<double>(q3));
+      }
+    }
   }
   if (BF16) {
     if (p.act == TNG_ACT_SILU) {
@@ -324,7 +354,7 @@ __device__ __forceinline__ void epi_stage(float* st, int lane, const uint32_t* v
 
 template <int BN, bool RES, bool F32, bool BF16>
 __device__ __forceinline__ void epi_tile_full(const GemmKernelParams& p, float* st, long long r0, int img0, bool rv_uniform,
-                                              uint32_t taddr, int tn, int lane, int hf) {
+                                              uint32_t taddr, int tn, int lane, int hf, long long stats_img) {
   const int cg = lane & 7, rsub = lane >> 3;
 #pragma unroll 1
   for (int c = hf * 32; c < BN; c += 64) {
@@ -334,7 +364,7 @@ __device__ __forceinline__ void epi_tile_full(const GemmKernelParams& p, float* 
     __syncwarp();  // previous chunk's smem reads are complete
     epi_stage(st, lane, v);
     __syncwarp();
-    epi_chunk_full<RES, F32, BF16>(p, st, r0, img0, rsub, cg, tn * BN + c + 4 * cg, rv_uniform);
+    epi_chunk_full<RES, F32, BF16>(p, st, r0, img0, rsub, cg, tn * BN + c + 4 * cg, rv_uniform, stats_img);
   }
 }
 
@@ -678,13 +708,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
         const long long r0 = row_base + ew * 32 + rsub;
         const int img0 = n0 + (ew * 32 + rsub) / rpi;
         const bool rv_uniform = (rpi % 32) == 0;   // the warp's 32 rows lie in one image
+        // image of this warp's 32 consecutive output rows for the GroupNorm statistics (stats_hw % 32 == 0: host check)
+        const long long simg = p.col_stats ? (row_base + ew * 32) / p.stats_hw : 0;
         switch (mode) {
-          case 2: epi_tile_full<BN, false, true, false>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf); break;
-          case 3: epi_tile_full<BN, true, true, false>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf); break;
-          case 4: epi_tile_full<BN, false, false, true>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf); break;
-          case 5: epi_tile_full<BN, true, false, true>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf); break;
-          case 6: epi_tile_full<BN, false, true, true>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf); break;
-          default: epi_tile_full<BN, true, true, true>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf); break;
+          case 2: epi_tile_full<BN, false, true, false>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf, simg); break;
+          case 3: epi_tile_full<BN, true, true, false>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf, simg); break;
+          case 4: epi_tile_full<BN, false, false, true>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf, simg); break;
+          case 5: epi_tile_full<BN, true, false, true>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf, simg); break;
+          case 6: epi_tile_full<BN, false, true, true>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf, simg); break;
+          default: epi_tile_full<BN, true, true, true>(p, st, r0, img0, rv_uniform, taddr, tn, lane, hf, simg); break;
         }
       }
       // all tcgen05.ld of this warp are complete (wait::ld): hand the accumulator stage back
@@ -854,6 +886,10 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   p.vec_ok = vec ? 1 : 0;
   p.fast_epi = (vec && d->Ncols % 4 == 0) ? 1 : 0;
   if ((d->act == TNG_ACT_GEGLU || d->act == TNG_ACT_GEGLU_TANH) && !vec) return set_error(TNG_EINVAL, "GEGLU epilogue needs 16-byte aligned output");
+  if (d->gn_stats) {
+    if (!d->out_f32 || d->stats_hw <= 0 || (static_cast<long long>(d->W) * d->H * d->NB) % d->stats_hw != 0)
+      return set_error(TNG_EINVAL, "gn_stats needs an fp32 output whose rows are whole images of stats_hw pixels");
+  }
 
   // cluster of 2 CTAs along M sharing (multicasting) the weight tile: whenever there are at least two M tiles
   // launch mode: 1 = single CTA, 2 = cluster-of-2 weight multicast, 3 = CTA pair (tcgen05 cta_group::2).
@@ -866,6 +902,16 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
     if (p.m_tiles < 2 || bn_tile < 64) cl = 1;
     if (cl != 1) p.ksplit = 1;   // split-K is implemented for the single-CTA mode only
     else if (p.ksplit > 1 && !p.fast_epi) p.ksplit = 1;
+  }
+  // GroupNorm statistics ride in the epilogue when every tile is full (the lean epilogue path), the warp's 32 rows lie
+  // in one image and the output is written exactly once; otherwise a separate pass over the output follows the GEMM
+  bool stats_after = false;
+  if (d->gn_stats) {
+    const bool full_m = (p.bh == 1 && p.bn == 1) ? (d->W % BM == 0) : (p.bn == 1 ? (d->H % p.bh == 0) : (d->NB % p.bn == 0));
+    const bool fused = full_m && (d->Ncols % bn_tile == 0) && p.fast_epi && p.ksplit == 1 && !d->accumulate &&
+                       (d->stats_hw % 32 == 0) && d->act != TNG_ACT_GEGLU && d->act != TNG_ACT_GEGLU_TANH;
+    if (fused) { p.col_stats = d->gn_stats; p.stats_hw = d->stats_hw; }
+    else stats_after = true;
   }
   // tensor maps
   CUtensorMap am[4];
@@ -892,12 +938,18 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
     cudaError_t e = cudaMemset2DAsync(d->out_f32, static_cast<size_t>(d->ld_f32) * 4, 0, static_cast<size_t>(d->Ncols) * 4, rows, st);
     if (e != cudaSuccess) return set_error(TNG_ECUDA, "cudaMemset2DAsync(split-K output): %s", cudaGetErrorString(e));
   }
+  int rc;
   switch (bn_tile) {
-    case 32: return launch_gemm<32>(am, bm, p, st, cl);
-    case 64: return launch_gemm<64>(am, bm, p, st, cl);
-    case 128: return launch_gemm<128>(am, bm, p, st, cl);
-    case 160: return launch_gemm<160>(am, bm, p, st, cl);
-    case 256: return launch_gemm<256>(am, bm, p, st, cl);
+    case 32: rc = launch_gemm<32>(am, bm, p, st, cl); break;
+    case 64: rc = launch_gemm<64>(am, bm, p, st, cl); break;
+    case 128: rc = launch_gemm<128>(am, bm, p, st, cl); break;
+    case 160: rc = launch_gemm<160>(am, bm, p, st, cl); break;
+    case 256: rc = launch_gemm<256>(am, bm, p, st, cl); break;
     default: return set_error(TNG_EINVAL, "block_n=%d unsupported", bn_tile);
   }
+  if (rc == TNG_OK && stats_after) {
+    const long long rows = static_cast<long long>(d->W) * d->H * d->NB;
+    rc = launch_col_stats(d->out_f32, TNG_DT_F32, d->Ncols, d->ld_f32, rows / d->stats_hw, d->stats_hw, d->gn_stats, st);
+  }
+  return rc;
 }

@@ -52,6 +52,7 @@ class GemmDesc(C.Structure):
         ("ldr", C.c_int64), ("alpha", C.c_float), ("accumulate", C.c_int32),
         ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int64),
         ("act", C.c_int32), ("act_param", C.c_float), ("split_off", C.c_int32), ("block_n", C.c_int32),
+        ("gn_stats", C.c_void_p), ("stats_hw", C.c_int64),
     ]
 
 
@@ -91,8 +92,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     sigs = {
         "tng_conv_gemm": [C.POINTER(GemmDesc), vp],
         "tng_attention": [C.POINTER(AttnDesc), vp],
-        "tng_groupnorm_stats": [vp, i32, i64, vp, i32, i64, i64, i64, i32, vp, vp],
-        "tng_groupnorm_apply": [vp, i32, i64, vp, i32, i64, i64, i64, i32, vp, vp, vp, f32, i32, vp, i64, i32, vp,
+        "tng_groupnorm_stats": [vp, i32, i64, i64, i64, i64, vp, vp],
+        "tng_groupnorm_apply": [vp, i32, i64, vp, vp, i32, i64, vp, i64, i64, i32, vp, vp, f32, i32, vp, i64, i32, vp,
                                 i64, i32, vp],
         "tng_layernorm": [vp, i64, i64, vp, vp, f32, vp, i64, i32, vp],
         "tng_rmsnorm": [vp, i64, i64, vp, f32, vp, i64, i32, vp, vp],
@@ -224,9 +225,12 @@ def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tens
               bias=None, rowvec=None, res=None, alpha: float = 1.0, accumulate: bool = False, out_f32=None,
               out_bf16=None, act: int = ACT_NONE, act_param: float = 0.0, split_off: int = 0, block_n: int = 0,
               ld_f32: Optional[int] = None, ld_bf16: Optional[int] = None, ldr: Optional[int] = None,
-              rowvec_ld: int = 0, algo_k: Optional[int] = None) -> None:
+              rowvec_ld: int = 0, algo_k: Optional[int] = None, gn_stats: Optional[torch.Tensor] = None,
+              stats_hw: int = 0) -> None:
     """Launch tng_conv_gemm. groups: (view, a_c0, dw, dh, b_k0, nkb). weight: bf16 [Ncols, Ktot].
-    algo_k: algorithmic reduction length (taps * Cin of the reference op) for the profiler's FLOP count."""
+    algo_k: algorithmic reduction length (taps * Cin of the reference op) for the profiler's FLOP count.
+    gn_stats: fp64 [images, Ncols, 2] per-channel GroupNorm accumulators of the fp32 output (zeroed by the caller),
+    images of stats_hw rows each."""
     lib = load()
     d = GemmDesc()
     require_cuda(weight, bias, rowvec, res, out_f32, out_bf16)
@@ -261,6 +265,10 @@ def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tens
     if out_bf16 is not None:
         d.ld_bf16 = out_bf16.stride(0) if ld_bf16 is None else ld_bf16
     d.act, d.act_param, d.split_off, d.block_n = act, act_param, split_off, block_n
+    if gn_stats is not None:
+        require_cuda(gn_stats)
+        assert gn_stats.dtype == torch.float64 and gn_stats.is_contiguous() and stats_hw > 0
+        d.gn_stats, d.stats_hw = gn_stats.data_ptr(), stats_hw
     if PROF.enabled:
         k_alg = algo_k if algo_k is not None else sum(g[5] for g in groups) * 64
         flops = 2.0 * W * H * NB * weight.shape[0] * k_alg
@@ -285,21 +293,28 @@ def attention(q, k, v, out, *, batch, heads, Lq, Lk, scale, q_col0=0, k_col0=0, 
 
 
 # --------------------------------------------------------------------------------------------------- norms etc.
-def groupnorm(x0, x1, NB, HW, groups, stats, gamma, beta, eps, act, y, *, split_off=0, raw=None, raw_split_off=0):
-    """GroupNorm(+act) of the channel concat [x0 | x1] (x1 may be None) -> bf16 y; optional raw bf16 copy."""
+def groupnorm_stats(x, NB, HW, stats):
+    """stats fp64 [NB, C, 2] += per-channel (sum, sum of squares) of x [NB*HW, C] — the stand-alone pass for tensors whose
+    statistics did not come out of the producing GEMM (conv_gemm(gn_stats=...))."""
+    require_cuda(x, stats)
+    Cc = x.shape[-1]
+    _call("gn_stats", NB * HW * Cc * _esz(x), load().tng_groupnorm_stats, x.data_ptr(), _dt(x), Cc, x.stride(0), NB, HW,
+          stats.data_ptr(), stream_ptr())
+
+
+def groupnorm(x0, st0, x1, st1, NB, HW, groups, gamma, beta, eps, act, y, *, split_off=0, raw=None, raw_split_off=0):
+    """GroupNorm(+act) of the channel concat [x0 | x1] (x1 may be None) -> bf16 y; optional raw bf16 copy. st0 / st1:
+    the per-channel fp64 statistics [NB, C, 2] of x0 / x1."""
     lib = load()
-    require_cuda(x0, x1, stats, gamma, beta, y, raw)
+    require_cuda(x0, x1, st0, st1, gamma, beta, y, raw)
     C0 = x0.shape[-1]
     C1 = 0 if x1 is None else x1.shape[-1]
-    s = stream_ptr()
     rows = NB * HW
     in_bytes = rows * (C0 * _esz(x0) + C1 * _esz(x1))
-    _call("gn_stats", in_bytes, lib.tng_groupnorm_stats, x0.data_ptr(), _dt(x0), C0, ptr(x1),
-          0 if x1 is None else _dt(x1), C1, NB, HW, groups, stats.data_ptr(), s)
     out_bytes = rows * (C0 + C1) * 2 * (2 if split_off else 1) * (2 if raw is not None else 1)
-    _call("gn_apply", in_bytes + out_bytes, lib.tng_groupnorm_apply, x0.data_ptr(), _dt(x0), C0, ptr(x1),
-          0 if x1 is None else _dt(x1), C1, NB, HW, groups, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps,
-          act, y.data_ptr(), y.stride(0), split_off, ptr(raw), 0 if raw is None else raw.stride(0), raw_split_off, s)
+    _call("gn_apply", in_bytes + out_bytes, lib.tng_groupnorm_apply, x0.data_ptr(), _dt(x0), C0, st0.data_ptr(), ptr(x1),
+          0 if x1 is None else _dt(x1), C1, ptr(st1), NB, HW, groups, gamma.data_ptr(), beta.data_ptr(), eps, act,
+          y.data_ptr(), y.stride(0), split_off, ptr(raw), 0 if raw is None else raw.stride(0), raw_split_off, stream_ptr())
 
 
 def layernorm(x, gamma, beta, eps, y, *, split_off=0):

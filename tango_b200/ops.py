@@ -157,10 +157,12 @@ def parity_views(x: torch.Tensor, NB: int, H: int, W: int, cin: int, split: bool
 
 def run_conv(pc: PackedConv, x: torch.Tensor, NB: int, H: int, W: int, *, sc_x: Optional[torch.Tensor] = None,
              rowvec=None, res=None, alpha: float = 1.0, accumulate: bool = False, out_f32=None, out_bf16=None,
-             act: int = L.ACT_NONE, act_param: float = 0.0, block_n: int = 0, rowvec_ld: int = 0) -> None:
+             act: int = L.ACT_NONE, act_param: float = 0.0, block_n: int = 0, rowvec_ld: int = 0,
+             gn_stats: Optional[torch.Tensor] = None, stats_hw: int = 0) -> None:
     """Convolution / linear of the bf16 operand x ([rows, cin] or [hi|lo]) on the (NB, H, W) grid.
 
-    For stride 2 (H, W) is the *input* grid; the output grid is (H/2, W/2)."""
+    For stride 2 (H, W) is the *input* grid; the output grid is (H/2, W/2).
+    gn_stats / stats_hw: per-channel GroupNorm accumulators of the fp32 output (see lib.conv_gemm)."""
     split = pc.split
     views: List[L.View] = []
     if pc.stride == 2:
@@ -187,7 +189,7 @@ def run_conv(pc: PackedConv, x: torch.Tensor, NB: int, H: int, W: int, *, sc_x: 
     L.conv_gemm(views, groups, pc.weight, Wo, Ho, NB, bias=pc.bias, rowvec=rowvec, res=res, alpha=alpha,
                 accumulate=accumulate, out_f32=out_f32, out_bf16=out_bf16, act=act, act_param=act_param,
                 split_off=so, block_n=block_n, rowvec_ld=rowvec_ld,
-                algo_k=len(pc.taps) * pc.cin + pc.cin_sc)
+                algo_k=len(pc.taps) * pc.cin + pc.cin_sc, gn_stats=gn_stats, stats_hw=stats_hw)
 
 
 def run_linear(pc: PackedConv, x: torch.Tensor, **kw) -> None:

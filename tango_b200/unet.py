@@ -54,6 +54,34 @@ class _Buffers:
         return buf
 
 
+class StatsArena:
+    """fp64 per-(image, channel) GroupNorm accumulators for every norm input of one forward, carved out of ONE buffer
+    so that a single fill zeroes them all at the start of the forward (slots keep their addresses: CUDA-graph safe).
+    A slot [NB, C, 2] belongs to one tensor; the GEMM that produces the tensor adds its column sums from the epilogue
+    (tng_conv_gemm gn_stats), the norm that consumes it — possibly twice: next layer and, as a skip connection, the up
+    path — reads them."""
+
+    def __init__(self, device, capacity: int):
+        self.buf = torch.zeros(max(capacity, 1), device=device, dtype=torch.float64)
+        self.slots: Dict[Tuple, Tuple[int, int]] = {}
+        self.used = 0
+
+    def slot(self, name: str, NB: int, C_: int) -> torch.Tensor:
+        key = (name, NB, C_)
+        hit = self.slots.get(key)
+        if hit is None:
+            n = NB * C_ * 2
+            if self.used + n > self.buf.numel():
+                raise L.TangoB200Error("GroupNorm statistics arena exhausted (internal sizing error)")
+            hit = (self.used, n)
+            self.slots[key] = hit
+            self.used += n
+        return self.buf[hit[0]:hit[0] + hit[1]].view(NB, C_, 2)
+
+    def zero(self):
+        self.buf[:max(self.used, 1)].zero_()
+
+
 class UNet2DConditionModel:
     """See module docstring. `precision`: "bf16" (perf) or "split" (parity)."""
 
@@ -242,8 +270,15 @@ class UNet2DConditionModel:
         P["temb_b"] = torch.cat([r.temb_b for r in res_all], 0).contiguous().to(dev)
         P["transformers"] = [t for b in P["down"] for t in b.attns] + [P["mid"].attn] + [t for b in P["up"] for t in b.attns]
         P["n_extra"] = max((len(t.extra) for t in P["transformers"]), default=0)
+        # channels that carry GroupNorm statistics in one forward: conv_in, both convs of every resnet, every
+        # transformer output, the up / down sampler convs (sizes the statistics arenas, one per batch size)
+        tr_all = list(P["transformers"]) + [x for t in P["transformers"] for x in t.extra]
+        P["stat_channels"] = (P["conv_in"].cout + sum(2 * r.cout for r in res_all) + sum(t.C for t in tr_all)
+                              + sum(b.down.cout for b in P["down"] if b.down is not None)
+                              + sum(b.up.cout for b in P["up"] if b.up is not None))
         self.P = P
         self._bufs = _Buffers(dev)
+        self._arenas: Dict[int, StatsArena] = {}
         self._cond = None
         self.pack_generation += 1
         self._packed = True
@@ -318,27 +353,39 @@ class UNet2DConditionModel:
             extra.append(SimpleNamespace(kvs=xk, bias=xb, Lk=Ln))
         self._cond = SimpleNamespace(kvs=kvs, bias=bias, Bu=Bu, Lk=Lk, extra=extra)
 
-    def _resnet(self, name, r, x0, x1, NB, H, W, temb, temb_ld):
+    def _arena(self, NB: int) -> StatsArena:
+        a = self._arenas.get(NB)
+        if a is None:
+            # 1.5x: under the CFG shared prefix a few tensors exist at half batch AND full batch
+            a = StatsArena(self.device, int(1.5 * 2 * NB * self.P["stat_channels"]) + 4096)
+            self._arenas[NB] = a
+        return a
+
+    def _resnet(self, name, r, x0, st0, x1, st1, NB, H, W, temb, temb_ld, ar: StatsArena):
+        """ResnetBlock2D (resnet.py:549-597) on rows; x0 / x1 (skip, may be None) arrive with their per-channel GroupNorm
+        statistics st0 / st1; returns (out, statistics of out)."""
         R, HW, s, sp = NB * H * W, H * W, self.s, self.split
-        P = self.P
         cin = r.cin
         a1 = self._buf("a", (R, cin * s), torch.bfloat16)
         has_sc = r.conv2.cin_sc > 0
         raw = self._buf("raw", (R, cin * s), torch.bfloat16) if has_sc else None
-        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
         eps = self.config.get("norm_eps", 1e-5)
-        L.groupnorm(x0, x1, NB, HW, 32, stats, r.n1w, r.n1b, eps, L.ACT_SILU, a1, split_off=cin if sp else 0, raw=raw,
+        L.groupnorm(x0, st0, x1, st1, NB, HW, 32, r.n1w, r.n1b, eps, L.ACT_SILU, a1, split_off=cin if sp else 0, raw=raw,
                     raw_split_off=cin if sp else 0)
         h1 = self._buf("h1", (R, r.cout), torch.float32)
-        run_conv(r.conv1, a1, NB, H, W, rowvec=temb[:, r.temb_off:], rowvec_ld=temb_ld, out_f32=h1)
+        st_h1 = ar.slot(name + "_h1", NB, r.cout)
+        run_conv(r.conv1, a1, NB, H, W, rowvec=temb[:, r.temb_off:], rowvec_ld=temb_ld, out_f32=h1, gn_stats=st_h1,
+                 stats_hw=HW)
         a2 = self._buf("a", (R, r.cout * s), torch.bfloat16)
-        L.groupnorm(h1, None, NB, HW, 32, stats, r.n2w, r.n2b, eps, L.ACT_SILU, a2, split_off=r.cout if sp else 0)
+        L.groupnorm(h1, st_h1, None, None, NB, HW, 32, r.n2w, r.n2b, eps, L.ACT_SILU, a2, split_off=r.cout if sp else 0)
         out = self._buf(name, (R, r.cout), torch.float32)
-        run_conv(r.conv2, a2, NB, H, W, sc_x=raw, res=None if has_sc else x0, out_f32=out)
-        return out
+        st_out = ar.slot(name, NB, r.cout)
+        run_conv(r.conv2, a2, NB, H, W, sc_x=raw, res=None if has_sc else x0, out_f32=out, gn_stats=st_out, stats_hw=HW)
+        return out, st_out
 
-    def _transformer(self, name, t, x, NB, H, W, kv, bias, Lk, shared_half: bool = False):
-        """shared_half: `x` holds only the first NB/2 images and stands for both CFG halves (identical latents and
+    def _transformer(self, name, t, x, st_x, NB, H, W, kv, bias, Lk, ar: StatsArena, shared_half: bool = False):
+        """Transformer2DModel (transformer_2d.py:214-321) on rows; returns (out, statistics of out).
+        shared_half: `x` holds only the first NB/2 images and stands for both CFG halves (identical latents and
         timestep): everything up to the self-attention output is computed once and duplicated before the
         cross-attention, the first place where the two halves see different data."""
         HW, s, sp, Cc = H * W, self.s, self.split, t.C
@@ -347,8 +394,7 @@ class UNet2DConditionModel:
         Rp, R = NBp * HW, NB * HW
         scale = 64 ** -0.5
         a = self._buf("a", (Rp, Cc * s), torch.bfloat16)
-        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
-        L.groupnorm(x, None, NBp, HW, 32, stats, t.nw, t.nb, 1e-6, L.ACT_NONE, a, split_off=so)
+        L.groupnorm(x, st_x, None, None, NBp, HW, 32, t.nw, t.nb, 1e-6, L.ACT_NONE, a, split_off=so)
         hs = self._buf("hs", (R, Cc), torch.float32)
         hsp = hs[:Rp]
         run_linear(t.proj_in, a, out_f32=hsp)
@@ -378,8 +424,9 @@ class UNet2DConditionModel:
         hsb = self._buf("hsb", (R, Cc * s), torch.bfloat16)
         run_linear(t.ff2, ff, res=hs, out_bf16=hsb)
         out = self._buf(name, (R, Cc), torch.float32)
-        run_linear(t.proj_out, hsb, res=x, out_f32=out)
-        return out
+        st_out = ar.slot(name, NB, Cc)
+        run_linear(t.proj_out, hsb, res=x, out_f32=out, gn_stats=st_out, stats_hw=HW)
+        return out, st_out
 
     def forward_rows(self, x_in: torch.Tensor, NB: int, H: int, W: int, temb: torch.Tensor, temb_ld: int,
                      out: Optional[torch.Tensor] = None, cfg_shared: bool = False) -> torch.Tensor:
@@ -400,59 +447,65 @@ class UNet2DConditionModel:
         R = NB * H * W
         shared = bool(cfg_shared) and NB % 2 == 0 and bool(P["down"][0].attns)
         NBp = NB // 2 if shared else NB
+        ar = self._arena(NB)
+        ar.zero()                       # one fill for the GroupNorm statistics of the whole forward
         h = self._buf("conv_in", (R, P["conv_in"].cout), torch.float32)
-        run_conv(P["conv_in"], x_in, NBp, H, W, out_f32=h[:NBp * H * W])
+        st = ar.slot("conv_in", NB, P["conv_in"].cout)
+        run_conv(P["conv_in"], x_in, NBp, H, W, out_f32=h[:NBp * H * W], gn_stats=st[:NBp], stats_hw=H * W)
         if shared:
             h[NBp * H * W:].copy_(h[:NBp * H * W])   # the conv_in output is also a skip connection (full batch)
-        skips = [h]
+            st[NBp:].copy_(st[:NBp])
+        skips = [(h, st)]
         ti = 0
         ch, cw = H, W
 
-        def extras(name, t, hh, idx):
+        def extras(name, t, hh, sth, idx):
             # Mustango: beat / chord transformers right after the text one (none for Tango)
             for n, tx in enumerate(t.extra):
                 e = c.extra[n]
-                hh = self._transformer(f"{name}x{n}", tx, hh, NB, ch, cw, e.kvs[idx], e.bias, e.Lk)
-            return hh
+                hh, sth = self._transformer(f"{name}x{n}", tx, hh, sth, NB, ch, cw, e.kvs[idx], e.bias, e.Lk, ar)
+            return hh, sth
 
         for i, blk in enumerate(P["down"]):
             for j, r in enumerate(blk.resnets):
                 first = shared and i == 0 and j == 0
                 if first:
-                    hp = self._resnet("d0r0", r, h[:NBp * H * W], None, NBp, ch, cw, temb, temb_ld)
-                    h = self._transformer("d0t0", blk.attns[0], hp, NB, ch, cw, c.kvs[ti], c.bias, c.Lk, shared_half=True)
-                    h = extras("d0t0", blk.attns[0], h, ti)
+                    hp, stp = self._resnet("d0r0", r, h[:NBp * H * W], st[:NBp], None, None, NBp, ch, cw, temb, temb_ld, ar)
+                    h, st = self._transformer("d0t0", blk.attns[0], hp, stp, NB, ch, cw, c.kvs[ti], c.bias, c.Lk, ar,
+                                              shared_half=True)
+                    h, st = extras("d0t0", blk.attns[0], h, st, ti)
                     ti += 1
-                    skips.append(h)
+                    skips.append((h, st))
                     continue
-                h = self._resnet(f"d{i}r{j}", r, h, None, NB, ch, cw, temb, temb_ld)
+                h, st = self._resnet(f"d{i}r{j}", r, h, st, None, None, NB, ch, cw, temb, temb_ld, ar)
                 if blk.attns:
-                    h = self._transformer(f"d{i}t{j}", blk.attns[j], h, NB, ch, cw, c.kvs[ti], c.bias, c.Lk)
-                    h = extras(f"d{i}t{j}", blk.attns[j], h, ti)
+                    h, st = self._transformer(f"d{i}t{j}", blk.attns[j], h, st, NB, ch, cw, c.kvs[ti], c.bias, c.Lk, ar)
+                    h, st = extras(f"d{i}t{j}", blk.attns[j], h, st, ti)
                     ti += 1
-                skips.append(h)
+                skips.append((h, st))
             if blk.down is not None:
                 Cc = blk.down.cin
                 xb = self._buf("a", (NB * ch * cw, Cc * s), torch.bfloat16)
                 L.cast_act(h, NB, ch, cw, xb, split_off=Cc if sp else 0)
                 hd = self._buf(f"d{i}ds", (NB * (ch // 2) * (cw // 2), blk.down.cout), torch.float32)
-                run_conv(blk.down, xb, NB, ch, cw, out_f32=hd)
+                st = ar.slot(f"d{i}ds", NB, blk.down.cout)
+                run_conv(blk.down, xb, NB, ch, cw, out_f32=hd, gn_stats=st, stats_hw=(ch // 2) * (cw // 2))
                 ch, cw = ch // 2, cw // 2
                 h = hd
-                skips.append(h)
+                skips.append((h, st))
         m = P["mid"]
-        h = self._resnet("m0", m.r0, h, None, NB, ch, cw, temb, temb_ld)
-        h = self._transformer("mt", m.attn, h, NB, ch, cw, c.kvs[ti], c.bias, c.Lk)
-        h = extras("mt", m.attn, h, ti)
+        h, st = self._resnet("m0", m.r0, h, st, None, None, NB, ch, cw, temb, temb_ld, ar)
+        h, st = self._transformer("mt", m.attn, h, st, NB, ch, cw, c.kvs[ti], c.bias, c.Lk, ar)
+        h, st = extras("mt", m.attn, h, st, ti)
         ti += 1
-        h = self._resnet("m1", m.r1, h, None, NB, ch, cw, temb, temb_ld)
+        h, st = self._resnet("m1", m.r1, h, st, None, None, NB, ch, cw, temb, temb_ld, ar)
         for i, blk in enumerate(P["up"]):
             for j, r in enumerate(blk.resnets):
-                skip = skips.pop()
-                h = self._resnet(f"u{i}r{j}", r, h, skip, NB, ch, cw, temb, temb_ld)
+                skip, st_skip = skips.pop()
+                h, st = self._resnet(f"u{i}r{j}", r, h, st, skip, st_skip, NB, ch, cw, temb, temb_ld, ar)
                 if blk.attns:
-                    h = self._transformer(f"u{i}t{j}", blk.attns[j], h, NB, ch, cw, c.kvs[ti], c.bias, c.Lk)
-                    h = extras(f"u{i}t{j}", blk.attns[j], h, ti)
+                    h, st = self._transformer(f"u{i}t{j}", blk.attns[j], h, st, NB, ch, cw, c.kvs[ti], c.bias, c.Lk, ar)
+                    h, st = extras(f"u{i}t{j}", blk.attns[j], h, st, ti)
                     ti += 1
             if blk.up is not None:
                 Cc = blk.up.cin
@@ -460,12 +513,12 @@ class UNet2DConditionModel:
                 L.cast_act(h, NB, ch, cw, xb, upsample2x=True, split_off=Cc if sp else 0)
                 ch, cw = 2 * ch, 2 * cw
                 hu = self._buf(f"u{i}us", (NB * ch * cw, blk.up.cout), torch.float32)
-                run_conv(blk.up, xb, NB, ch, cw, out_f32=hu)
+                st = ar.slot(f"u{i}us", NB, blk.up.cout)
+                run_conv(blk.up, xb, NB, ch, cw, out_f32=hu, gn_stats=st, stats_hw=ch * cw)
                 h = hu
         Cc = cfg["block_out_channels"][0]
         a = self._buf("a", (R, Cc * s), torch.bfloat16)
-        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
-        L.groupnorm(h, None, NB, H * W, 32, stats, P["norm_out"][0], P["norm_out"][1], cfg.get("norm_eps", 1e-5),
+        L.groupnorm(h, st, None, None, NB, H * W, 32, P["norm_out"][0], P["norm_out"][1], cfg.get("norm_eps", 1e-5),
                     L.ACT_SILU, a, split_off=Cc if sp else 0)
         if out is None:
             out = self._buf("unet_out", (R, P["conv_out"].cout), torch.float32)

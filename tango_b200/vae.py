@@ -22,7 +22,7 @@ import torch
 from . import lib as L
 from .ops import PackedConv, run_conv, run_linear
 from .synth import HIFIGAN_CONFIG, VAE_CONFIG, vae_decoder_param_shapes, vae_encoder_param_shapes
-from .unet import _Buffers
+from .unet import StatsArena, _Buffers
 
 
 class DiagonalGaussianDistribution:
@@ -177,40 +177,55 @@ class AutoencoderKL:
                 st.blocks.append(rb)
             V.stages.append(st)
         V.conv_post = PackedConv(sd["vocoder.conv_post.weight"], sd["vocoder.conv_post.bias"], split=sp, device=dev)
+        res_all = [P.mid1, P.mid2] + [r for blk in P.up for r in blk.res]
+        P.stat_channels = (P.conv_in.cout + sum(2 * r.cout for r in res_all) + P.attn.C
+                           + sum(blk.up.cout for blk in P.up if blk.up is not None))
         self.P, self.V = P, V
         self._bufs = _Buffers(dev)
+        self._arenas = {}
         self._packed = True
 
     def _buf(self, name, shape, dtype):
         return self._bufs.get(name, shape, dtype)
 
+    def _arena(self, tag: str, NB: int, channels: int) -> StatsArena:
+        """GroupNorm statistics arena of one decode / encode call (see unet.StatsArena)."""
+        key = (tag, NB)
+        a = self._arenas.get(key)
+        if a is None:
+            a = StatsArena(self._device, 2 * NB * channels + 4096)
+            self._arenas[key] = a
+        a.zero()
+        return a
+
     # ------------------------------------------------------------------------------------------ decoder
-    def _resnet(self, name, r, x, NB, H, W):
-        R, s, sp = NB * H * W, self.s, self.split
+    def _resnet(self, name, r, x, st, NB, H, W, ar):
+        """modules.py:155-175 on rows; (x, st) = input and its per-channel GroupNorm statistics; returns (out, stats)."""
+        R, s, sp, HW = NB * H * W, self.s, self.split, H * W
         a1 = self._buf("a", (R, r.cin * s), torch.bfloat16)
         has_sc = r.conv2.cin_sc > 0
         raw = self._buf("raw", (R, r.cin * s), torch.bfloat16) if has_sc else None
-        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
-        L.groupnorm(x, None, NB, H * W, 32, stats, r.n1w, r.n1b, 1e-6, L.ACT_SILU, a1, split_off=r.cin if sp else 0,
+        L.groupnorm(x, st, None, None, NB, HW, 32, r.n1w, r.n1b, 1e-6, L.ACT_SILU, a1, split_off=r.cin if sp else 0,
                     raw=raw, raw_split_off=r.cin if sp else 0)
         h1 = self._buf("h1", (R, r.cout), torch.float32)
-        run_conv(r.conv1, a1, NB, H, W, out_f32=h1)
+        st_h1 = ar.slot(name + "_h1", NB, r.cout)
+        run_conv(r.conv1, a1, NB, H, W, out_f32=h1, gn_stats=st_h1, stats_hw=HW)
         a2 = self._buf("a", (R, r.cout * s), torch.bfloat16)
-        L.groupnorm(h1, None, NB, H * W, 32, stats, r.n2w, r.n2b, 1e-6, L.ACT_SILU, a2, split_off=r.cout if sp else 0)
+        L.groupnorm(h1, st_h1, None, None, NB, HW, 32, r.n2w, r.n2b, 1e-6, L.ACT_SILU, a2, split_off=r.cout if sp else 0)
         out = self._buf(name, (R, r.cout), torch.float32)
-        run_conv(r.conv2, a2, NB, H, W, sc_x=raw, res=None if has_sc else x, out_f32=out)
-        return out
+        st_out = ar.slot(name, NB, r.cout)
+        run_conv(r.conv2, a2, NB, H, W, sc_x=raw, res=None if has_sc else x, out_f32=out, gn_stats=st_out, stats_hw=HW)
+        return out, st_out
 
-    def _attn(self, x, NB, H, W, t=None):
+    def _attn(self, x, st, NB, H, W, ar, t=None):
         """modules.py:204-230: softmax(q k^T / sqrt(C)) v over the H*W positions of each image, one head.
-        `t`: packed attention weights (default: the decoder's mid block)."""
+        `t`: packed attention weights (default: the decoder's mid block). Returns (out, stats of out)."""
         t = self.P.attn if t is None else t
         R, HW, s, sp, Cc = NB * H * W, H * W, self.s, self.split, t.C
         if HW % 64:
             raise L.TangoB200Error("VAE attention needs H*W to be a multiple of 64")
         a = self._buf("a", (R, Cc * s), torch.bfloat16)
-        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
-        L.groupnorm(x, None, NB, HW, 32, stats, t.nw, t.nb, 1e-6, L.ACT_NONE, a, split_off=Cc if sp else 0)
+        L.groupnorm(x, st, None, None, NB, HW, 32, t.nw, t.nb, 1e-6, L.ACT_NONE, a, split_off=Cc if sp else 0)
         qkv = self._buf("vqkv", (R, 3 * Cc * s), torch.bfloat16)  # [q k v | q_lo k_lo v_lo]
         run_linear(t.qkv, a, out_bf16=qkv)
         S = self._buf("vS", (HW, HW), torch.float32)
@@ -241,8 +256,9 @@ class AutoencoderKL:
             ob = o[b * HW:(b + 1) * HW]
             L.conv_gemm([pv], g, vt, HW, 1, 1, out_bf16=ob, split_off=Cc if sp else 0)
         out = self._buf("vattn", (R, Cc), torch.float32)
-        run_linear(t.proj, o, res=x, out_f32=out)
-        return out
+        st_out = ar.slot("vattn", NB, Cc)
+        run_linear(t.proj, o, res=x, out_f32=out, gn_stats=st_out, stats_hw=HW)
+        return out, st_out
 
     def decode_rows(self, z_rows: torch.Tensor, NB: int, H: int, W: int) -> torch.Tensor:
         """z_rows fp32 [NB*H*W, 8] (channels-last latents) -> mel fp32 [NB*4H*4W, 1] (== [NB*4H, 64] for W = 16)."""
@@ -254,27 +270,29 @@ class AutoencoderKL:
         L.linear_f32(z_rows, P.pq_w, P.pq_b, z1)
         zb = self._buf("vzb", (R, zc * s), torch.bfloat16)
         L.cast_act(z1, NB, H, W, zb, split_off=zc if sp else 0)
+        ar = self._arena("dec", NB, P.stat_channels)
         h = self._buf("vconv_in", (R, P.conv_in.cout), torch.float32)
-        run_conv(P.conv_in, zb, NB, H, W, out_f32=h)
-        h = self._resnet("vmid1", P.mid1, h, NB, H, W)
-        h = self._attn(h, NB, H, W)
-        h = self._resnet("vmid2", P.mid2, h, NB, H, W)
+        st = ar.slot("vconv_in", NB, P.conv_in.cout)
+        run_conv(P.conv_in, zb, NB, H, W, out_f32=h, gn_stats=st, stats_hw=H * W)
+        h, st = self._resnet("vmid1", P.mid1, h, st, NB, H, W, ar)
+        h, st = self._attn(h, st, NB, H, W, ar)
+        h, st = self._resnet("vmid2", P.mid2, h, st, NB, H, W, ar)
         ch, cw = H, W
         for li, blk in enumerate(P.up):
             for bi, r in enumerate(blk.res):
-                h = self._resnet(f"vup{li}_{bi}", r, h, NB, ch, cw)
+                h, st = self._resnet(f"vup{li}_{bi}", r, h, st, NB, ch, cw, ar)
             if blk.up is not None:
                 Cc = blk.up.cin
                 xb = self._buf("a", (NB * 4 * ch * cw, Cc * s), torch.bfloat16)
                 L.cast_act(h, NB, ch, cw, xb, upsample2x=True, split_off=Cc if sp else 0)
                 ch, cw = 2 * ch, 2 * cw
                 hu = self._buf(f"vups{li}", (NB * ch * cw, blk.up.cout), torch.float32)
-                run_conv(blk.up, xb, NB, ch, cw, out_f32=hu)
+                st = ar.slot(f"vups{li}", NB, blk.up.cout)
+                run_conv(blk.up, xb, NB, ch, cw, out_f32=hu, gn_stats=st, stats_hw=ch * cw)
                 h = hu
         Cc = h.shape[1]
         a = self._buf("a", (NB * ch * cw, Cc * s), torch.bfloat16)
-        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
-        L.groupnorm(h, None, NB, ch * cw, 32, stats, P.no_w, P.no_b, 1e-6, L.ACT_SILU, a, split_off=Cc if sp else 0)
+        L.groupnorm(h, st, None, None, NB, ch * cw, 32, P.no_w, P.no_b, 1e-6, L.ACT_SILU, a, split_off=Cc if sp else 0)
         mel = self._buf("vmel", (NB * ch * cw, P.conv_out.cout), torch.float32)
         run_conv(P.conv_out, a, NB, ch, cw, out_f32=mel)
         return mel
@@ -346,6 +364,9 @@ class AutoencoderKL:
         E.conv_out = conv("encoder.conv_out")
         E.q_w = sd["quant_conv.weight"].float().reshape(sd["quant_conv.weight"].shape[0], -1).contiguous().to(dev)
         E.q_b = f32("quant_conv.bias")
+        eres = [r for blk in E.down for r in blk.res] + [E.mid1, E.mid2]
+        E.stat_channels = (E.conv_in.cout + sum(2 * r.cout for r in eres) + E.attn.C
+                           + sum(blk.down.cout for blk in E.down if blk.down is not None))
         self.E = E
         self._epacked = True
 
@@ -359,27 +380,29 @@ class AutoencoderKL:
         x8[:, :mel_rows.shape[1]] = mel_rows
         xb = self._buf("a", (R, E.cin_pad * s), torch.bfloat16)
         L.cast_act(x8, NB, H, W, xb, split_off=E.cin_pad if sp else 0)
+        ar = self._arena("enc", NB, E.stat_channels)
         h = self._buf("econv_in", (R, E.conv_in.cout), torch.float32)
-        run_conv(E.conv_in, xb, NB, H, W, out_f32=h)
+        st = ar.slot("econv_in", NB, E.conv_in.cout)
+        run_conv(E.conv_in, xb, NB, H, W, out_f32=h, gn_stats=st, stats_hw=H * W)
         ch, cw = H, W
         for li, blk in enumerate(E.down):
             for bi, r in enumerate(blk.res):
-                h = self._resnet(f"edown{li}_{bi}", r, h, NB, ch, cw)
+                h, st = self._resnet(f"edown{li}_{bi}", r, h, st, NB, ch, cw, ar)
             if blk.down is not None:
                 Cc = blk.down.cin
                 xb = self._buf("a", (NB * ch * cw, Cc * s), torch.bfloat16)
                 L.cast_act(h, NB, ch, cw, xb, split_off=Cc if sp else 0)
                 hd = self._buf(f"edown{li}_ds", (NB * (ch // 2) * (cw // 2), blk.down.cout), torch.float32)
-                run_conv(blk.down, xb, NB, ch, cw, out_f32=hd)
+                st = ar.slot(f"edown{li}_ds", NB, blk.down.cout)
+                run_conv(blk.down, xb, NB, ch, cw, out_f32=hd, gn_stats=st, stats_hw=(ch // 2) * (cw // 2))
                 ch, cw = ch // 2, cw // 2
                 h = hd
-        h = self._resnet("emid1", E.mid1, h, NB, ch, cw)
-        h = self._attn(h, NB, ch, cw, E.attn)
-        h = self._resnet("emid2", E.mid2, h, NB, ch, cw)
+        h, st = self._resnet("emid1", E.mid1, h, st, NB, ch, cw, ar)
+        h, st = self._attn(h, st, NB, ch, cw, ar, E.attn)
+        h, st = self._resnet("emid2", E.mid2, h, st, NB, ch, cw, ar)
         Cc = h.shape[1]
         a = self._buf("a", (NB * ch * cw, Cc * s), torch.bfloat16)
-        stats = self._buf("gnstats", (NB * 32 * 2,), torch.float64)
-        L.groupnorm(h, None, NB, ch * cw, 32, stats, E.no_w, E.no_b, 1e-6, L.ACT_SILU, a, split_off=Cc if sp else 0)
+        L.groupnorm(h, st, None, None, NB, ch * cw, 32, E.no_w, E.no_b, 1e-6, L.ACT_SILU, a, split_off=Cc if sp else 0)
         mom = self._buf("emom", (NB * ch * cw, E.conv_out.cout), torch.float32)
         run_conv(E.conv_out, a, NB, ch, cw, out_f32=mom)
         out = self._buf("emoments", (NB * ch * cw, E.q_w.shape[0]), torch.float32)

@@ -34,7 +34,8 @@ def _gather_view(v, n_idx, h_idx, w_idx, c0, nk):
 
 
 def spec_conv_gemm(views, groups, weight, W, H, NB, *, bias=None, rowvec=None, res=None, alpha=1.0, accumulate=False,
-                   out_f32=None, out_bf16=None, act=ACT_NONE, act_param=0.0, split_off=0, block_n=0, rowvec_ld=0, **_):
+                   out_f32=None, out_bf16=None, act=ACT_NONE, act_param=0.0, split_off=0, block_n=0, rowvec_ld=0,
+                   gn_stats=None, stats_hw=0, **_):
     rows = NB * H * W
     r = torch.arange(rows)
     n_idx, h_idx, w_idx = r // (H * W), (r // W) % H, r % W
@@ -63,6 +64,10 @@ def spec_conv_gemm(views, groups, weight, W, H, NB, *, bias=None, rowvec=None, r
         if accumulate:        # the accumulated value is also what the bf16 output (if any) is derived from
             y = y + out_f32[:, :Ncols].double()
         out_f32[:, :Ncols] = y.float()
+        if gn_stats is not None:   # per-(image, channel) sums of the STORED fp32 output are ADDED to the accumulators
+            yi = out_f32[:, :Ncols].double().view(rows // stats_hw, stats_hw, Ncols)
+            gn_stats[..., 0] += yi.sum(1)
+            gn_stats[..., 1] += (yi * yi).sum(1)
     if out_bf16 is not None:
         z = y.float()
         if act == ACT_SILU:
@@ -101,10 +106,27 @@ def _act(z, act, act_param=0.0):
     return z
 
 
-def spec_groupnorm(x0, x1, NB, HW, groups, stats, gamma, beta, eps, act, y, *, split_off=0, raw=None, raw_split_off=0):
+def spec_groupnorm_stats(x, NB, HW, stats):
+    xi = x.double().view(NB, HW, x.shape[-1])
+    stats[..., 0] += xi.sum(1)
+    stats[..., 1] += (xi * xi).sum(1)
+
+
+def spec_groupnorm(x0, st0, x1, st1, NB, HW, groups, gamma, beta, eps, act, y, *, split_off=0, raw=None, raw_split_off=0):
+    """Normalisation with the group mean / variance taken from the per-channel accumulators (sum, sum of squares), as
+    the kernel does: mean = S / n, var = Q / n - mean^2 over the channels of the group in the concat [x0 | x1]."""
     x = x0.float() if x1 is None else torch.cat([x0.float(), x1.float()], dim=-1)
     C_ = x.shape[1]
-    z = F.group_norm(x.view(NB, HW, C_).permute(0, 2, 1), groups, gamma, beta, eps).permute(0, 2, 1).reshape(NB * HW, C_)
+    st = st0 if x1 is None else torch.cat([st0, st1], dim=1)            # [NB, C, 2]
+    cpg = C_ // groups
+    gs = st.view(NB, groups, cpg, 2).sum(2)
+    n = float(HW * cpg)
+    mean = gs[..., 0] / n
+    var = (gs[..., 1] / n - mean * mean).clamp_min(0.0)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    mean_c = mean.float().repeat_interleave(cpg, 1)[:, None, :]
+    rstd_c = rstd.float().repeat_interleave(cpg, 1)[:, None, :]
+    z = ((x.view(NB, HW, C_) - mean_c) * rstd_c * gamma + beta).reshape(NB * HW, C_)
     _store_bf16(y, _act(z, act), split_off)
     if raw is not None:
         _store_bf16(raw, x, raw_split_off)
@@ -265,6 +287,6 @@ def spec_log_clamp(x, y, floor=1e-5):
 
 SPEC = {"stft_frames": spec_stft_frames, "stft_magnitude": spec_stft_magnitude, "log_clamp": spec_log_clamp,
         "softmax_rows": spec_softmax_rows, "transpose_bf16": spec_transpose_bf16, "convt_gather": spec_convt_gather,
-        "tanh_to_i16": spec_tanh_to_i16, "sched_step": spec_sched_step, "conv_gemm": spec_conv_gemm, "groupnorm": spec_groupnorm, "layernorm": spec_layernorm, "rmsnorm": spec_rmsnorm,
+        "tanh_to_i16": spec_tanh_to_i16, "sched_step": spec_sched_step, "conv_gemm": spec_conv_gemm, "groupnorm": spec_groupnorm, "groupnorm_stats": spec_groupnorm_stats, "layernorm": spec_layernorm, "rmsnorm": spec_rmsnorm,
         "gather_rows": spec_gather_rows, "cast_act": spec_cast_act, "attention": spec_attention,
         "rel_attention": spec_rel_attention, "timestep_embedding": spec_timestep_embedding, "linear_f32": spec_linear_f32}

@@ -8,6 +8,7 @@ import torch.nn.functional as F
 
 from tango_b200 import lib as L
 from tango_b200 import ops
+from tango_b200.ops import PackedConv, run_conv
 
 pytestmark = pytest.mark.gpu
 
@@ -259,10 +260,15 @@ def test_groupnorm(cuda, C0, C1, act, eps):
     Cc = C0 + C1
     gamma = torch.randn(Cc, generator=g).to(cuda)
     beta = torch.randn(Cc, generator=g).to(cuda)
-    stats = torch.empty(NB * 32 * 2, device=cuda, dtype=torch.float64)
+    st0 = torch.zeros(NB, C0, 2, device=cuda, dtype=torch.float64)
+    st1 = torch.zeros(NB, C1, 2, device=cuda, dtype=torch.float64) if C1 else None
+    L.groupnorm_stats(x0, NB, HW, st0)                     # the stand-alone per-channel statistics pass
+    if C1:
+        L.groupnorm_stats(x1, NB, HW, st1)
+    assert rel_err(st0[..., 0].float(), x0.view(NB, HW, C0).sum(1)) < 1e-5
     y = torch.empty(NB * HW, 2 * Cc, device=cuda, dtype=torch.bfloat16)
     raw = torch.empty(NB * HW, 2 * Cc, device=cuda, dtype=torch.bfloat16)
-    L.groupnorm(x0, x1, NB, HW, 32, stats, gamma, beta, eps, act, y, split_off=Cc, raw=raw, raw_split_off=Cc)
+    L.groupnorm(x0, st0, x1, st1, NB, HW, 32, gamma, beta, eps, act, y, split_off=Cc, raw=raw, raw_split_off=Cc)
     xc = x0 if x1 is None else torch.cat([x0, x1.float()], dim=1)
     ref = F.group_norm(xc.view(NB, HW, Cc).permute(0, 2, 1).double(), 32, gamma.double(), beta.double(), eps)
     if act == L.ACT_SILU:
@@ -272,6 +278,33 @@ def test_groupnorm(cuda, C0, C1, act, eps):
     assert rel_err(y[:, :Cc].float() + y[:, Cc:].float(), ref) < 2e-5
     assert rel_err(y[:, :Cc], ref) < 5e-3
     assert rel_err(raw[:, :Cc].float() + raw[:, Cc:].float(), xc) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(16, 8, 4, 128, 320, 1, "full tiles: epilogue"),     # NB, H, W, Cin, Cout, taps
+                                   (4, 16, 16, 64, 640, 9, "3x3 conv, full tiles: epilogue"),
+                                   (3, 4, 8, 64, 64, 9, "partial tiles: pass after the GEMM"),
+                                   (2, 2, 32, 1280, 1280, 9, "under-filled split-K launch: pass after the GEMM")])
+def test_conv_gemm_emits_groupnorm_statistics(cuda, shape):
+    """tng_conv_gemm(gn_stats=...): per-(image, channel) sum / sum of squares of the fp32 output, accumulated from the
+    epilogue (or by the follow-up pass when tiles are partial / split-K), must equal the column sums of what was stored."""
+    NB, H, W, Cin, Cout, taps, _ = shape
+    g = torch.Generator(device="cpu").manual_seed(Cout + taps)
+    k = 3 if taps == 9 else 1
+    w = torch.randn(Cout, Cin, k, k, generator=g) * (Cin * taps) ** -0.5
+    b = torch.randn(Cout, generator=g)
+    x = torch.randn(NB * H * W, Cin, generator=g)
+    res = torch.randn(NB * H * W, Cout, generator=g).to(cuda)
+    pc = PackedConv(w if k == 3 else w[:, :, 0, 0], b, split=False, device=cuda)
+    out = torch.zeros(NB * H * W, Cout, device=cuda)
+    st = torch.zeros(NB, Cout, 2, device=cuda, dtype=torch.float64)
+    run_conv(pc, bf(x).to(cuda), NB, H, W, res=res if taps == 1 else None, out_f32=out, gn_stats=st, stats_hw=H * W)
+    torch.cuda.synchronize()
+    o = out.double().view(NB, H * W, Cout)
+    assert rel_err(st[..., 0], o.sum(1)) < 1e-6 and rel_err(st[..., 1], (o * o).sum(1)) < 1e-6
+    # accumulators ADD: a second launch doubles them
+    run_conv(pc, bf(x).to(cuda), NB, H, W, res=res if taps == 1 else None, out_f32=out, gn_stats=st, stats_hw=H * W)
+    torch.cuda.synchronize()
+    assert rel_err(st[..., 0], 2 * o.sum(1)) < 1e-6
 
 
 @pytest.mark.parametrize("Cc", [64, 320, 1280])
