@@ -196,51 +196,65 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, 
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// one warp per row; the row is cached in registers (NI float4 per lane, C <= 128 * NI) so the variance is the exact
-// two-pass form; NI is a template parameter so that no predicated-off iterations are issued.
-template <int NI, bool RMS>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long long rows, int C, const float* gamma,
-                                                         const float* beta, float eps, __nv_bfloat16* y, long long ld_y,
-                                                         int split_off, float* yf) {
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  const int Q = C / 4;
-  float4 v[NI];
-  float s = 0.f;
-  const float* xr = x + row * C;
+// One warp per row, the row cached in registers (NI float4 per lane, C <= 128 * NI), so the variance is the exact
+// two-pass form; NI is a template parameter so that no predicated-off iterations are issued. The grid is sized to the
+// machine (a few CTAs per SM) and every warp walks rows with a stride, loading row r + stride while it normalises row
+// r: the HBM latency of the next row hides behind the arithmetic and the stores of the current one.
+template <int NI>
+__device__ __forceinline__ void ln_load_row(const float* xr, int lane, int Q, float4* v) {
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
     const int q = lane + i * 32;
     v[i] = (q < Q) ? *reinterpret_cast<const float4*>(xr + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
-  const float mean = RMS ? 0.f : warp_sum(s) / C;   // RMS (T5LayerNorm): no centring, no bias
-  float sq = 0.f;
+}
+
+template <int NI, bool RMS>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long long rows, int C, const float* gamma,
+                                                         const float* beta, float eps, __nv_bfloat16* y, long long ld_y,
+                                                         int split_off, float* yf) {
+  const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int Q = C / 4;
+  float4 v[NI], nx[NI];
+  ln_load_row<NI>(x + row * C, lane, Q, v);
+  for (; row < rows; row += nwarps) {
+    const long long rn = row + nwarps;
+    if (rn < rows) ln_load_row<NI>(x + rn * C, lane, Q, nx);
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NI; ++i) {
-    const int q = lane + i * 32;
-    if (q < Q) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      sq += a * a + b * b + c * c + d * d;
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / C + eps);
-  __nv_bfloat16* yr = y + row * ld_y;
+    for (int i = 0; i < NI; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = RMS ? 0.f : warp_sum(s) / C;   // RMS (T5LayerNorm): no centring, no bias
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < NI; ++i) {
-    const int q = lane + i * 32;
-    if (q < Q) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + q * 4));
-      const float4 b = RMS ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(beta + q * 4));
-      float4 o;
-      o.x = (v[i].x - mean) * rstd * g.x + b.x;
-      o.y = (v[i].y - mean) * rstd * g.y + b.y;
-      o.z = (v[i].z - mean) * rstd * g.z + b.z;
-      o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      if (y) store4_split(yr + q * 4, o, split_off);
-      if (yf) *reinterpret_cast<float4*>(yf + row * C + q * 4) = o;   // optional fp32 copy (dense rows)
+    for (int i = 0; i < NI; ++i) {
+      const int q = lane + i * 32;
+      if (q < Q) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += a * a + b * b + c * c + d * d;
+      }
     }
+    const float rstd = rsqrtf(warp_sum(sq) / C + eps);
+    __nv_bfloat16* yr = y + row * ld_y;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int q = lane + i * 32;
+      if (q < Q) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + q * 4));
+        const float4 b = RMS ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(beta + q * 4));
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (y) store4_split(yr + q * 4, o, split_off);
+        if (yf) *reinterpret_cast<float4*>(yf + row * C + q * 4) = o;   // optional fp32 copy (dense rows)
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) v[i] = nx[i];
   }
 }
 
@@ -610,6 +624,14 @@ static inline int gn_rows_for(long long NB, long long HW) {
   return static_cast<int>(rows);
 }
 
+// LayerNorm grid: one warp per row up to 4 CTAs of `wpb` warps per SM, then the warps stride over the rows
+static inline unsigned ln_grid(long long rows, int wpb) {
+  long long g = (rows + wpb - 1) / wpb;
+  const long long cap = 4LL * num_sms();
+  if (g > cap) g = cap;
+  return static_cast<unsigned>(g < 1 ? 1 : g);
+}
+
 static inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -677,7 +699,7 @@ extern "C" int tng_layernorm(const float* x, int64_t rows, int64_t C, const floa
                              void* y, int64_t ld_y, int32_t split_off, void* stream) {
   if (!x || !y || !gamma || !beta || C % 4 || C > 2048 || ld_y % 4 || split_off % 4) return set_error(TNG_EINVAL, "layernorm: C=%lld unsupported", (long long)C);
   const int wpb = 8;
-  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  const unsigned grid = ln_grid(rows, wpb);
   const int ni = (int)((C / 4 + 31) / 32);
 #define TNG_LN(NI) layernorm_kernel<NI, false><<<grid, wpb * 32, 0, ST(stream)>>>(x, rows, (int)C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off, nullptr)
   if (ni <= 1) TNG_LN(1);
@@ -695,7 +717,7 @@ extern "C" int tng_rmsnorm(const float* x, int64_t rows, int64_t C, const float*
                            int32_t split_off, float* y_f32, void* stream) {
   if (!x || (!y && !y_f32) || !gamma || C % 4 || C > 2048 || ld_y % 4 || split_off % 4) return set_error(TNG_EINVAL, "rmsnorm: C=%lld unsupported", (long long)C);
   const int wpb = 8;
-  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  const unsigned grid = ln_grid(rows, wpb);
   const int ni = (int)((C / 4 + 31) / 32);
   const float* beta = nullptr;
 #define TNG_RMS(NI) layernorm_kernel<NI, true><<<grid, wpb * 32, 0, ST(stream)>>>(x, rows, (int)C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off, y_f32)

@@ -63,18 +63,24 @@ struct GemmKernelParams {
   long long stats_hw;
 };
 
-// PAIR: cta_group::2 — each CTA of the pair stages its own 128 A rows and only HALF of the weight tile
-template <int BN, bool PAIR = false>
+// PAIR: cta_group::2 — each CTA of the pair stages its own 128 A rows and only HALF of the weight tile.
+// NH = 2 (pair mode only): the pair owns a 256 x (2 BN) output tile — two BN-wide accumulators fed from the SAME A
+// stage — which halves the operand bytes each SM pulls from L2 per FLOP once more (the measured main-loop limiter).
+template <int BN, bool PAIR = false, int NH = 1>
 struct GemmCfg {
-  static constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
+  static constexpr int B_HALF_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // one BN-wide weight tile (this CTA's share)
+  static constexpr int B_TILE_BYTES = NH * B_HALF_BYTES;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // per epilogue warp: 32 x 32 fp32 swizzled transpose tile
   static constexpr int STAGES_RAW = (227 * 1024 - EPI_BYTES - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (4 * BN <= 128) ? 128 : (4 * BN <= 256) ? 256 : 512;  // one CTA per SM: take what helps
-  // accumulator stages in TMEM: as many as fit (2 for N tile 256, 3 for 160, 4 for <= 128): extra stages absorb the
-  // wake-up latency of the epilogue warps when the main loop of a tile is short (K = 320 linears)
+  // accumulator slots (BN columns each) in TMEM: as many as fit (2 for N tile 256, 3 for 160, 4 for <= 128): extra
+  // slots absorb the wake-up latency of the epilogue warps when the main loop of a tile is short (K = 320 linears).
+  // With NH = 2 a tile takes two consecutive slots of the ring (3 slots at BN = 160: the next tile's main loop starts
+  // as soon as the epilogue has drained the first half of the current one).
   static constexpr int NACC = (TMEM_COLS / BN) > 4 ? 4 : (TMEM_COLS / BN);
+  static_assert(NH == 1 || NACC >= 3, "two-accumulator tiles need a ring of at least three slots");
   static constexpr int ACC_STRIDE = BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
 };
@@ -514,9 +520,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUtensorMap amap1,
                const __grid_constant__ CUtensorMap amap2, const __grid_constant__ CUtensorMap amap3,
                const __grid_constant__ CUtensorMap bmap, const __grid_constant__ GemmKernelParams p) {
-  constexpr bool PAIR = (CL == 3);
+  constexpr bool PAIR = (CL == 3 || CL == 4);
+  constexpr int NH = (CL == 4) ? 2 : 1;      // BN-wide accumulators per tile (CL = 4: 256 x 2 BN pair tiles)
   constexpr int CLUSTER = (CL == 1) ? 1 : 2;
-  using Cfg = GemmCfg<BN, PAIR>;
+  using Cfg = GemmCfg<BN, PAIR, NH>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment (checked below)
   uint8_t* sA = smem;
@@ -596,8 +603,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
             // both CTAs load into their own smem; all bytes are credited to the LEADER's full barrier
             if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             tma_load_4d_2sm(sA + stage * A_TILE_BYTES, am, &full_bar[stage], g.a_c0 + kb * BK, w0 + g.dw, h0 + g.dh, n0);
-            tma_load_2d_2sm(sB + stage * Cfg::B_TILE_BYTES, &bmap, &full_bar[stage], g.b_k0 + kb * BK,
-                            tn * BN + crank * (BN / 2));
+#pragma unroll
+            for (int nh = 0; nh < NH; ++nh)
+              tma_load_2d_2sm(sB + stage * Cfg::B_TILE_BYTES + nh * Cfg::B_HALF_BYTES, &bmap, &full_bar[stage],
+                              g.b_k0 + kb * BK, (tn * NH + nh) * BN + crank * (BN / 2));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -622,31 +631,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     uint32_t phase = 0;
     int it = 0;
     for (int tile = work0; tile < total_tiles; tile += work_stride, ++it) {
-      const int as = it % NACC;
-      const uint32_t aphase = (it / NACC) & 1;
-      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      // accumulator slot of half-tile j = it * NH + nh: j % NACC, in its (j / NACC)-th use
+      uint32_t d_tmem[NH];
+#pragma unroll
+      for (int nh = 0; nh < NH; ++nh) {
+        const int j = it * NH + nh;
+        mbar_wait(&tempty_bar[j % NACC], ((j / NACC) & 1) ^ 1);
+        d_tmem[nh] = tmem_base + (j % NACC) * Cfg::ACC_STRIDE;
+      }
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
       const int sp = tile % p.ksplit;
       const int nk = (sp + 1) * p.total_kiters / p.ksplit - sp * p.total_kiters / p.ksplit;
       for (int ki = 0; ki < nk; ++ki) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * A_TILE_BYTES), 16, 1024);
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_TILE_BYTES), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the (>>4) start-address field
-          if (PAIR) umma_bf16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
-          else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+        for (int nh = 0; nh < NH; ++nh) {
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_TILE_BYTES + nh * Cfg::B_HALF_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the (>>4) start-address field
+            if (PAIR) umma_bf16_2cta(d_tmem[nh], adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem[nh], adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          }
         }
         if (CL == 1) umma_commit(&empty_bar[stage]);
         else if (CL == 2) umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>(3));  // frees the slot in both CTAs
         else umma_commit2_mc(&empty_bar[stage], static_cast<uint16_t>(3));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (PAIR) umma_commit2_mc(&tfull_bar[as], static_cast<uint16_t>(3));  // each CTA drains its own 128 rows
-      else umma_commit(&tfull_bar[as]);
+#pragma unroll
+      for (int nh = 0; nh < NH; ++nh) {
+        const int j = it * NH + nh;
+        if (PAIR) umma_commit2_mc(&tfull_bar[j % NACC], static_cast<uint16_t>(3));  // each CTA drains its own 128 rows
+        else umma_commit(&tfull_bar[j % NACC]);
+      }
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue (8 warps)
@@ -659,7 +679,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     int it = 0;
     for (int tile = work0; tile < total_tiles; tile += work_stride, ++it) {
       const int sp = tile % p.ksplit, t2 = tile / p.ksplit;
-      const int tm = (t2 / p.n_tiles) * CLUSTER + crank, tn = t2 % p.n_tiles;
+      const int tm = (t2 / p.n_tiles) * CLUSTER + crank, tn0 = t2 % p.n_tiles;
       const int tw = tm % p.tiles_w;
       const int th = (tm / p.tiles_w) % p.tiles_h;
       const int tb = tm / (p.tiles_w * p.tiles_h);
@@ -671,12 +691,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
       else if (p.bn == 1) nvalid = min(p.bh, p.H - h0) * p.bw;
       else nvalid = min(p.bn, p.NB - n0) * p.bh * p.bw;
       const int rpi = p.bw * p.bh;  // rows of one image inside a tile
-      const int as = it % NACC;
-      const uint32_t aphase = (it / NACC) & 1;
+      if (tm >= p.m_tiles) nvalid = 0;  // padding tile of an odd cluster tail
+#pragma unroll 1
+      for (int nh = 0; nh < NH; ++nh) {
+      // half-tile j: accumulator slot j % NACC in its (j / NACC)-th use; output columns of N tile tn * NH + nh
+      const int j = it * NH + nh;
+      const int as = j % NACC;
+      const uint32_t aphase = (j / NACC) & 1;
+      const int tn = tn0 * NH + nh;
       const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (static_cast<uint32_t>(ew * 32) << 16);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      if (tm >= p.m_tiles) nvalid = 0;  // padding tile of an odd cluster tail
       const bool full = p.fast_epi && (nvalid == BM) && ((tn + 1) * BN <= p.Ncols);
       if (p.ksplit > 1) {
         epi_tile_splitk<BN>(p, st, row_base, n0, rpi, nvalid, sp, taddr, tn, lane, ew, hf);
@@ -726,6 +751,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
         if (PAIR && crank != 0) mbar_arrive_remote(&tempty_bar[as], 0);  // the leader's MMA issuer owns the accumulators
         else mbar_arrive(&tempty_bar[as]);
       }
+      }  // nh
     }
   }
 
@@ -743,7 +769,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
 template <int BN, int CL>
 static int launch_gemm_cl(const CUtensorMap* am, const CUtensorMap& bm, const GemmKernelParams& p, cudaStream_t st) {
   constexpr int CLUSTER = (CL == 1) ? 1 : 2;
-  using Cfg = GemmCfg<BN, CL == 3>;
+  using Cfg = GemmCfg<BN, (CL == 3 || CL == 4), (CL == 4) ? 2 : 1>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -776,6 +802,10 @@ static int launch_gemm_cl(const CUtensorMap* am, const CUtensorMap& bm, const Ge
 
 template <int BN>
 static int launch_gemm(const CUtensorMap* am, const CUtensorMap& bm, const GemmKernelParams& p, cudaStream_t st, int cl) {
+  if (cl == 4) {
+    if constexpr (BN == 160 || BN == 128) return launch_gemm_cl<BN, 4>(am, bm, p, st);
+    else return set_error(TNG_EINVAL, "two-accumulator pair tiles exist for N tiles 128 and 160 only");
+  }
   if (cl == 3) return launch_gemm_cl<BN, 3>(am, bm, p, st);
   return cl == 2 ? launch_gemm_cl<BN, 2>(am, bm, p, st) : launch_gemm_cl<BN, 1>(am, bm, p, st);
 }
@@ -891,23 +921,32 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
       return set_error(TNG_EINVAL, "gn_stats needs an fp32 output whose rows are whole images of stats_hw pixels");
   }
 
-  // cluster of 2 CTAs along M sharing (multicasting) the weight tile: whenever there are at least two M tiles
-  // launch mode: 1 = single CTA, 2 = cluster-of-2 weight multicast, 3 = CTA pair (tcgen05 cta_group::2).
-  // TNG_GEMM_CLUSTER overrides the default for experiments.
+  // Launch mode. 1 = one CTA per SM; 4 = CTA pair (tcgen05 cta_group::2) on a 256 x (2 x bn_tile) output tile: each SM
+  // stages its 128 A rows and HALF of two weight tiles per K block, i.e. half the L2 -> SM operand bytes per FLOP of
+  // mode 1 — the measured main-loop limiter of the long-reduction 3x3 convolutions. Chosen when the reduction is long
+  // enough to hide the (half-overlapped) epilogue, every tile is full and the launch fills at least half the pairs.
+  // Modes 2 (cluster-of-2 weight multicast) and 3 (pair on a 256 x bn_tile tile) are kept for A/B measurements
+  // (TNG_GEMM_CLUSTER = 1..3 forces a mode; bench.py refuses to run with it set).
+  const bool full_m = (p.bh == 1 && p.bn == 1) ? (d->W % BM == 0) : (p.bn == 1 ? (d->H % p.bh == 0) : (d->NB % p.bn == 0));
   int cl = 1;
   {
     static int force = -1;
     if (force < 0) { const char* e = getenv("TNG_GEMM_CLUSTER"); force = e ? atoi(e) : 0; }
-    if (force >= 1 && force <= 3) cl = force;
+    const bool geglu = d->act == TNG_ACT_GEGLU || d->act == TNG_ACT_GEGLU_TANH;
+    const bool pair2_ok = (bn_tile == 160 || bn_tile == 128) && d->Ncols % (2 * bn_tile) == 0 && full_m &&
+                          p.m_tiles % 2 == 0 && p.fast_epi && !geglu && p.ksplit == 1 && p.total_kiters >= 16 &&
+                          static_cast<long long>(p.m_tiles / 2) * (d->Ncols / (2 * bn_tile)) * 2 >= num_sms() / 2;
+    if (force == 0 || force == 4) cl = pair2_ok ? 4 : 1;
+    else if (force >= 1 && force <= 3) cl = force;
     if (p.m_tiles < 2 || bn_tile < 64) cl = 1;
     if (cl != 1) p.ksplit = 1;   // split-K is implemented for the single-CTA mode only
     else if (p.ksplit > 1 && !p.fast_epi) p.ksplit = 1;
+    if (cl == 4) p.n_tiles = static_cast<int>(d->Ncols / (2 * bn_tile));
   }
   // GroupNorm statistics ride in the epilogue when every tile is full (the lean epilogue path), the warp's 32 rows lie
   // in one image and the output is written exactly once; otherwise a separate pass over the output follows the GEMM
   bool stats_after = false;
   if (d->gn_stats) {
-    const bool full_m = (p.bh == 1 && p.bn == 1) ? (d->W % BM == 0) : (p.bn == 1 ? (d->H % p.bh == 0) : (d->NB % p.bn == 0));
     const bool fused = full_m && (d->Ncols % bn_tile == 0) && p.fast_epi && p.ksplit == 1 && !d->accumulate &&
                        (d->stats_hw % 32 == 0) && d->act != TNG_ACT_GEGLU && d->act != TNG_ACT_GEGLU_TANH;
     if (fused) { p.col_stats = d->gn_stats; p.stats_hw = d->stats_hw; }

@@ -489,8 +489,7 @@ class Tango:
         """decode_first_stage + decode_to_waveform without leaving channels-last rows (tango.py:47-48)."""
         B, Cl, H, W = latents.shape
         rows = latents.float().permute(0, 2, 3, 1).reshape(B * H * W, Cl).contiguous()
-        mel = self.vae.decode_rows(rows, B, H, W)                       # [B*4H*4W, 1] == [B*4H, 64]
-        _, wi = self.vae.vocoder_rows(mel.view(B * 4 * H, 4 * W), B, 4 * H)
+        _, wi = self.vae.decode_rows_to_waveform(rows, B, H, W, use_cuda_graph=self.model.use_cuda_graph)
         return wi.cpu().numpy()
 
     def generate(self, prompt, steps=100, guidance=3, samples=1, disable_progress=True, **kw):

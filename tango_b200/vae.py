@@ -183,6 +183,7 @@ class AutoencoderKL:
         self.P, self.V = P, V
         self._bufs = _Buffers(dev)
         self._arenas = {}
+        self._graphs = {}
         self._packed = True
 
     def _buf(self, name, shape, dtype):
@@ -296,6 +297,37 @@ class AutoencoderKL:
         mel = self._buf("vmel", (NB * ch * cw, P.conv_out.cout), torch.float32)
         run_conv(P.conv_out, a, NB, ch, cw, out_f32=mel)
         return mel
+
+    def decode_rows_to_waveform(self, z_rows: torch.Tensor, NB: int, H: int, W: int, use_cuda_graph: bool = True):
+        """decode_first_stage + decode_to_waveform on rows: fp32 [NB*H*W, 8] latents -> (wave fp32 [NB, L], int16
+        [NB, L]) on the device. The ~600 launches of the decoder and the vocoder are captured once per shape into a CUDA
+        graph (all operands live in persistent buffers) and replayed afterwards."""
+        self._pack()
+        if not use_cuda_graph:
+            mel = self.decode_rows(z_rows, NB, H, W)
+            return self.vocoder_rows(mel.view(NB * 4 * H, 4 * W), NB, 4 * H)
+        key = (NB, H, W)
+        st = self._graphs.get(key)
+        if st is None:
+            zin = self._buf("graph_zin", tuple(z_rows.shape), torch.float32)
+            zin.copy_(z_rows)
+
+            def run():
+                mel = self.decode_rows(zin, NB, H, W)
+                return self.vocoder_rows(mel.view(NB * 4 * H, 4 * W), NB, 4 * H)
+
+            run()                               # warm-up: allocates every scratch buffer, sets kernel attributes
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                wf, wi = run()
+            st = SimpleNamespace(graph=g, zin=zin, wf=wf, wi=wi)
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = st
+        st.zin.copy_(z_rows)
+        st.graph.replay()
+        return st.wf, st.wi
 
     def decode_first_stage(self, z: torch.Tensor, predict_cids=False, force_not_quantize=False) -> torch.Tensor:
         """(B, 8, T/4, 16) latents -> (B, 1, T, 64) log-mel (autoencoder.py:116-124)."""

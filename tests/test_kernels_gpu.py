@@ -68,6 +68,41 @@ def test_conv3x3(cuda, NB, H, W, Cin, Cout):
     assert rel_err(of, ref) < 2e-5
 
 
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,split", [(5, 32, 64, 128, 320, False),     # 40 pair tiles x 1 N pair
+                                                   (20, 16, 16, 128, 640, False),    # 20 x 2, W < 128 pixel tiles
+                                                   (20, 8, 64, 64, 256, True),       # N tile 128 x 2, hi/lo K groups
+                                                   (4, 64, 16, 320, 1280, False)])   # 16 x 4, the UNet level-2 shape
+def test_conv3x3_pair_tiles_two_accumulators(cuda, NB, H, W, Cin, Cout, split):
+    """Launches large enough for the CTA-pair mode (tcgen05 cta_group::2, 256 x 2*BN output tile per pair, two
+    accumulators in a 3-slot TMEM ring): full epilogue with bias, time-embedding row vector, residual, fp32 + bf16
+    (SiLU) outputs and the GroupNorm statistics, against torch."""
+    g = torch.Generator(device="cpu").manual_seed(NB * 100 + Cout)
+    x = torch.randn(NB, Cin, H, W, generator=g).to(cuda)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)).to(cuda)
+    b = torch.randn(Cout, generator=g).to(cuda)
+    temb = torch.randn(NB, Cout, generator=g).to(cuda)
+    res = torch.randn(NB * H * W, Cout, generator=g).to(cuda)
+    pc = ops.PackedConv(w, b, split=split, device=cuda)
+    rows = nhwc_rows(x)
+    xin = to_split(rows) if split else bf(rows)
+    of = torch.full((NB * H * W, Cout), float("nan"), device=cuda)
+    ob = torch.zeros(NB * H * W, Cout * (2 if split else 1), device=cuda, dtype=torch.bfloat16)
+    st = torch.zeros(NB, Cout, 2, device=cuda, dtype=torch.float64)
+    ops.run_conv(pc, xin, NB, H, W, rowvec=temb, res=res, out_f32=of, out_bf16=ob, act=L.ACT_SILU, gn_stats=st,
+                 stats_hw=H * W)
+    if split:
+        ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).float()
+    else:
+        ref = F.conv2d(bf(x).float(), bf(w).float(), b, padding=1)
+    ref = nhwc_rows(ref + temb[:, :, None, None]) + res
+    torch.cuda.synchronize()
+    assert rel_err(of, ref) < 3e-5
+    got_b = ob[:, :Cout].float() + (ob[:, Cout:].float() if split else 0)
+    assert rel_err(got_b, F.silu(ref)) < (3e-5 if split else 5e-3)
+    o = of.double().view(NB, H * W, Cout)
+    assert rel_err(st[..., 0], o.sum(1)) < 1e-6 and rel_err(st[..., 1], (o * o).sum(1)) < 1e-6
+
+
 def test_conv3x3_split_matches_fp32(cuda):
     NB, H, W, Cin, Cout = 2, 16, 16, 128, 160
     g = torch.Generator(device="cpu").manual_seed(5)
