@@ -126,20 +126,25 @@ __device__ __forceinline__ void gn_apply_rows(const void* base, long long idx0, 
 template <bool SILU, bool SPLIT, bool RAW>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, int C0, const double* stats0,
                                                         const void* x1, int dt1, int C1, const double* stats1,
-                                                        long long HW, int groups, int tpg,
+                                                        long long HW, int groups, int tpg, int slab,
                                                         const float* gamma, const float* beta, float eps,
                                                         __nv_bfloat16* y, long long ld_y, int split_off,
                                                         __nv_bfloat16* raw, long long ld_raw, int raw_split_off, int GN_ROWS) {
+  // A CTA owns GN_ROWS pixels of image blockIdx.y and the channel slab [c_lo, c_lo + slab) (whole groups, a multiple of
+  // 4 channels): it reduces the per-channel accumulators of ITS groups only, so wide concatenated inputs (up to 2560
+  // channels) do not make every CTA re-read the statistics of the whole tensor.
   __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.y;
   const int C = C0 + C1;
   const int cpg = C / groups;
+  const int c_lo = blockIdx.z * slab;
+  const int g_lo = c_lo / cpg, n_g = slab / cpg;
   {
-    // group statistics from the per-channel accumulators of the two sources: tpg threads (a power of two <= 32, lanes of
-    // one warp) share a group
-    const int g = threadIdx.x / tpg, sub = threadIdx.x % tpg;
+    // tpg threads (a power of two <= 32, lanes of one warp) share a group
+    const int gi = threadIdx.x / tpg, sub = threadIdx.x % tpg;
+    const int g = g_lo + gi;
     double sum = 0.0, sq = 0.0;
-    if (g < groups) {
+    if (gi < n_g) {
       for (int c = g * cpg + sub; c < (g + 1) * cpg; c += tpg) {
         const double* sp = (c < C0) ? stats0 + (static_cast<long long>(n) * C0 + c) * 2
                                     : stats1 + (static_cast<long long>(n) * C1 + (c - C0)) * 2;
@@ -151,25 +156,25 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, 
       sum += __shfl_xor_sync(0xffffffffu, sum, o);
       sq += __shfl_xor_sync(0xffffffffu, sq, o);
     }
-    if (g < groups && sub == 0) {
+    if (gi < n_g && sub == 0) {
       const double cnt = static_cast<double>(HW) * cpg;
       const double mean = sum / cnt;
       double var = sq / cnt - mean * mean;
       if (var < 0.0) var = 0.0;
-      s_mean[g] = static_cast<float>(mean);
-      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      s_mean[gi] = static_cast<float>(mean);
+      s_rstd[gi] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
     }
   }
   __syncthreads();
   const long long r0 = static_cast<long long>(blockIdx.x) * GN_ROWS;
   const int nrows = static_cast<int>((HW - r0) < GN_ROWS ? (HW - r0) : GN_ROWS);
-  const int Q = C / 4;
+  const int Q = slab / 4;
   const int QT = Q < 256 ? Q : 256;
   const int RL = 256 / QT;
   const int rl = threadIdx.x / QT;
   if (rl >= RL) return;
   for (int q = threadIdx.x - rl * QT; q < Q; q += QT) {
-    const int c = q * 4;
+    const int c = c_lo + q * 4;
     const bool first = c < C0;
     const void* base = first ? x0 : x1;
     const int dt = first ? dt0 : dt1;
@@ -181,9 +186,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, 
     const float gm[4] = {g4.x, g4.y, g4.z, g4.w}, bt[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int g = (c + j) / cpg;
-      sc[j] = s_rstd[g] * gm[j];
-      sh[j] = bt[j] - s_mean[g] * sc[j];
+      const int gi = (c + j) / cpg - g_lo;
+      sc[j] = s_rstd[gi] * gm[j];
+      sh[j] = bt[j] - s_mean[gi] * sc[j];
     }
     const long long rowb = n * HW + r0;
     __nv_bfloat16* yp = y + rowb * ld_y + c;
@@ -671,15 +676,22 @@ extern "C" int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, cons
   if (!x0 || !stats0 || (x1 && !stats1) || !y || groups <= 0 || groups > 64 || C % groups || C0 % 4 || (x1 && C1 % 4) ||
       ld_y % 4 || split_off % 4 || C > 8192)
     return set_error(TNG_EINVAL, "groupnorm_apply: bad shape");
-  const int gn_rows = gn_rows_for(NB, HW);
-  dim3 grid((unsigned)((HW + gn_rows - 1) / gn_rows), (unsigned)NB);
   if (act != TNG_ACT_NONE && act != TNG_ACT_SILU) return set_error(TNG_EINVAL, "groupnorm_apply: act must be NONE or SILU");
+  // channel slab per CTA: whole groups, a multiple of 4 channels, about 256-320 channels when the tensor is wider
+  const int cpg = (int)(C / groups);
+  int gps = 1;                                   // groups per slab
+  while ((gps * cpg) % 4 != 0 && gps < groups) ++gps;
+  while (gps * 2 * cpg <= 320 && groups % (gps * 2) == 0) gps *= 2;
+  if ((gps * cpg) % 4 != 0 || groups % gps != 0) { gps = groups; }   // fall back: one slab = all channels
+  const int slab = gps * cpg, nslabs = groups / gps;
+  const int gn_rows = gn_rows_for(NB * nslabs, HW);
+  dim3 grid((unsigned)((HW + gn_rows - 1) / gn_rows), (unsigned)NB, (unsigned)nslabs);
   int tpg = 1;
-  while (tpg * 2 * groups <= 256 && tpg < 32) tpg *= 2;
+  while (tpg * 2 * gps <= 256 && tpg < 32) tpg *= 2;
   const bool silu = act == TNG_ACT_SILU, split = split_off > 0, hasraw = raw_bf16 != nullptr;
 #define TNG_GN_LAUNCH(S, P, R)                                                                                           \
   gn_apply_kernel<S, P, R><<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, stats0, x1, dt1, x1 ? (int)C1 : 0, stats1, HW, \
-                                                          groups, tpg, gamma, beta, eps,                                  \
+                                                          groups, tpg, slab, gamma, beta, eps,                            \
                                                           reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off,           \
                                                           reinterpret_cast<__nv_bfloat16*>(raw_bf16), ld_raw,             \
                                                           raw_split_off, gn_rows)

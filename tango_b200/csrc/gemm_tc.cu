@@ -924,7 +924,8 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   // Launch mode. 1 = one CTA per SM; 4 = CTA pair (tcgen05 cta_group::2) on a 256 x (2 x bn_tile) output tile: each SM
   // stages its 128 A rows and HALF of two weight tiles per K block, i.e. half the L2 -> SM operand bytes per FLOP of
   // mode 1 — the measured main-loop limiter of the long-reduction 3x3 convolutions. Chosen when the reduction is long
-  // enough to hide the (half-overlapped) epilogue, every tile is full and the launch fills at least half the pairs.
+  // enough (>= 36 K blocks: measured, a K = 1280 linear with an fp32 residual is slower in this mode) to hide the
+  // half-overlapped epilogue, every tile is full and the launch fills at least half the pairs.
   // Modes 2 (cluster-of-2 weight multicast) and 3 (pair on a 256 x bn_tile tile) are kept for A/B measurements
   // (TNG_GEMM_CLUSTER = 1..3 forces a mode; bench.py refuses to run with it set).
   const bool full_m = (p.bh == 1 && p.bn == 1) ? (d->W % BM == 0) : (p.bn == 1 ? (d->H % p.bh == 0) : (d->NB % p.bn == 0));
@@ -934,7 +935,7 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
     if (force < 0) { const char* e = getenv("TNG_GEMM_CLUSTER"); force = e ? atoi(e) : 0; }
     const bool geglu = d->act == TNG_ACT_GEGLU || d->act == TNG_ACT_GEGLU_TANH;
     const bool pair2_ok = (bn_tile == 160 || bn_tile == 128) && d->Ncols % (2 * bn_tile) == 0 && full_m &&
-                          p.m_tiles % 2 == 0 && p.fast_epi && !geglu && p.ksplit == 1 && p.total_kiters >= 16 &&
+                          p.m_tiles % 2 == 0 && p.fast_epi && !geglu && p.ksplit == 1 && p.total_kiters >= 36 &&
                           static_cast<long long>(p.m_tiles / 2) * (d->Ncols / (2 * bn_tile)) * 2 >= num_sms() / 2;
     if (force == 0 || force == 4) cl = pair2_ok ? 4 : 1;
     else if (force >= 1 && force <= 3) cl = force;
