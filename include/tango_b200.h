@@ -132,6 +132,15 @@ typedef struct {
 
 int tng_attention(const tng_attn_desc* d, void* stream);
 
+/* tng_attention_wide — tcgen05 flash attention for ONE head of width `dim` = 512, Lq = Lk = L, no mask: the AudioLDM VAE
+ * AttnBlock  softmax(q k^T * scale) v  over the H*W positions of each image
+ * (audioldm/variational_autoencoder/modules.py:204-230). q / k / v: bf16 rows = batch*L positions, the operand at columns
+ * [col0, col0 + dim) of a row-major matrix with leading dimension ld (elements); out: bf16 [batch*L, ld_o], columns
+ * [0, dim). The [L, L] score matrix stays on the SM (S, P and O live in tensor memory). L must be a multiple of 128. */
+int tng_attention_wide(const void* q, int64_t ld_q, int32_t q_col0, const void* k, int64_t ld_k, int32_t k_col0,
+                       const void* v, int64_t ld_v, int32_t v_col0, void* out, int64_t ld_o, int32_t batch, int32_t L,
+                       int32_t dim, float scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU) over channels-last input that may be the channel concat of two tensors (skip connection).
  * Replaces: nn.GroupNorm + SiLU in ResnetBlock2D (resnet.py:555-557,581-587), conv_norm_out

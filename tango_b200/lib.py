@@ -24,7 +24,7 @@ SYMBOLS = [
     "tng_groupnorm_stats", "tng_groupnorm_apply", "tng_layernorm", "tng_cast_act", "tng_softmax_rows",
     "tng_transpose_bf16", "tng_sched_step", "tng_timestep_embedding", "tng_linear_f32", "tng_convt_gather",
     "tng_tanh_to_i16", "tng_rmsnorm", "tng_gather_rows", "tng_rel_attention", "tng_stft_frames", "tng_stft_magnitude",
-    "tng_log_clamp",
+    "tng_log_clamp", "tng_attention_wide",
 ]
 
 
@@ -110,6 +110,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "tng_stft_frames": [vp, i64, i64, i32, vp, vp, i64, vp],
         "tng_stft_magnitude": [vp, i64, i32, i64, vp, i64, i32, vp, vp, f32, vp],
         "tng_log_clamp": [vp, i64, f32, vp, vp],
+        "tng_attention_wide": [vp, i64, i32, vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, i32, f32, vp],
     }
     for name, argt in sigs.items():
         fn = getattr(lib, name)
@@ -290,6 +291,15 @@ def attention(q, k, v, out, *, batch, heads, Lq, Lk, scale, q_col0=0, k_col0=0, 
     d.batch, d.heads, d.Lq, d.Lk, d.scale, d.nsplit = batch, heads, Lq, Lk, scale, nsplit
     PROF.timed("attention_tc", 4.0 * batch * heads * Lq * Lk * 64, 0,
                lambda: check(lib.tng_attention(C.byref(d), stream_ptr()), "tng_attention"))
+
+
+def attention_wide(q, k, v, out, *, batch, L, dim, scale, q_col0=0, k_col0=0, v_col0=0) -> None:
+    """One-head flash attention of width `dim` (= 512: the VAE AttnBlock); see tng_attention_wide."""
+    require_cuda(q, k, v, out)
+    PROF.timed("attention_wide", 4.0 * batch * L * L * dim, 0,
+               lambda: check(load().tng_attention_wide(q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0,
+                                                       v.data_ptr(), v.stride(0), v_col0, out.data_ptr(), out.stride(0),
+                                                       batch, L, dim, scale, stream_ptr()), "tng_attention_wide"))
 
 
 # --------------------------------------------------------------------------------------------------- norms etc.

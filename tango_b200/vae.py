@@ -7,7 +7,8 @@ they belong to the training path).
 
 decoder:  modules.py:650-683 (conv_in, mid res-attn-res, 3 up levels x 3 ResnetBlocks, nearest x2 + conv, norm_out,
           swish, conv_out) — same GroupNorm / tcgen05 conv kernels as the UNet. The single-head 512-wide mid
-          AttnBlock (modules.py:204-230) runs as tcgen05 GEMMs  S = q k^T  ->  row softmax  ->  P v  per image.
+          AttnBlock (modules.py:204-230) is one flash-attention launch for the whole batch (tng_attention_wide: S, P and
+          O in tensor memory, the scores never reach HBM); the parity mode keeps GEMM -> row softmax -> GEMM per image.
 vocoder:  hifigan/models.py:149-165 — Conv1d stacks as 1-D implicit GEMMs with leaky-ReLU / residual / 3-way average
           fused in the epilogues, ConvTranspose1d as GEMM + overlap-add gather, tanh -> int16 in one HBM kernel.
 """
@@ -229,10 +230,19 @@ class AutoencoderKL:
         L.groupnorm(x, st, None, None, NB, HW, 32, t.nw, t.nb, 1e-6, L.ACT_NONE, a, split_off=Cc if sp else 0)
         qkv = self._buf("vqkv", (R, 3 * Cc * s), torch.bfloat16)  # [q k v | q_lo k_lo v_lo]
         run_linear(t.qkv, a, out_bf16=qkv)
+        o = self._buf("vo", (R, Cc * s), torch.bfloat16)
+        if not sp and Cc == 512 and HW % 128 == 0:
+            # perf mode: one flash-attention launch for the whole batch, the [HW, HW] scores never leave the SM
+            L.attention_wide(qkv, qkv, qkv, o, batch=NB, L=HW, dim=Cc, scale=float(Cc) ** -0.5, q_col0=0, k_col0=Cc,
+                             v_col0=2 * Cc)
+            out = self._buf("vattn", (R, Cc), torch.float32)
+            st_out = ar.slot("vattn", NB, Cc)
+            run_linear(t.proj, o, res=x, out_f32=out, gn_stats=st_out, stats_hw=HW)
+            return out, st_out
+        # parity mode (hi/lo split operands): scores through HBM, image by image — GEMM -> row softmax -> GEMM
         S = self._buf("vS", (HW, HW), torch.float32)
         Pm = self._buf("vP", (HW, HW * s), torch.bfloat16)
         vt = self._buf("vVt", (Cc, HW * s), torch.bfloat16)
-        o = self._buf("vo", (R, Cc * s), torch.bfloat16)
         nkb_c, nkb_hw = Cc // 64, HW // 64
         lo = 3 * Cc
         for b in range(NB):

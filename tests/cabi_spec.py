@@ -175,6 +175,12 @@ def spec_attention(q, k, v, out, *, batch, heads, Lq, Lk, scale, q_col0=0, k_col
     _store_bf16(out, o, split_off)
 
 
+def spec_attention_wide(q, k, v, out, *, batch, L, dim, scale, q_col0=0, k_col0=0, v_col0=0):
+    qh, kh, vh = (t[:, c:c + dim].float().view(batch, L, dim) for t, c in ((q, q_col0), (k, k_col0), (v, v_col0)))
+    o = (qh @ kh.transpose(1, 2) * scale).softmax(-1) @ vh
+    out[:, :dim] = o.reshape(batch * L, dim).to(torch.bfloat16)
+
+
 def spec_rel_attention(qkv, relbias, kbias, out, *, batch, heads, L, q_col0, k_col0, v_col0, split_off=0):
     inner = heads * 64
     q, k, v = (qkv[:, c:c + inner].view(batch, L, heads, 64).transpose(1, 2) for c in (q_col0, k_col0, v_col0))
@@ -285,7 +291,7 @@ def spec_log_clamp(x, y, floor=1e-5):
     y.copy_(torch.log(torch.clamp(x.float(), min=floor)))
 
 
-SPEC = {"stft_frames": spec_stft_frames, "stft_magnitude": spec_stft_magnitude, "log_clamp": spec_log_clamp,
+SPEC = {"attention_wide": spec_attention_wide, "stft_frames": spec_stft_frames, "stft_magnitude": spec_stft_magnitude, "log_clamp": spec_log_clamp,
         "softmax_rows": spec_softmax_rows, "transpose_bf16": spec_transpose_bf16, "convt_gather": spec_convt_gather,
         "tanh_to_i16": spec_tanh_to_i16, "sched_step": spec_sched_step, "conv_gemm": spec_conv_gemm, "groupnorm": spec_groupnorm, "groupnorm_stats": spec_groupnorm_stats, "layernorm": spec_layernorm, "rmsnorm": spec_rmsnorm,
         "gather_rows": spec_gather_rows, "cast_act": spec_cast_act, "attention": spec_attention,

@@ -342,6 +342,26 @@ def test_conv_gemm_emits_groupnorm_statistics(cuda, shape):
     assert rel_err(st[..., 0], 2 * o.sum(1)) < 1e-6
 
 
+@pytest.mark.parametrize("B,Lq,spread", [(2, 256, 1.0), (1, 1024, 1.0), (2, 384, 6.0)])
+def test_attention_wide_d512(cuda, B, Lq, spread):
+    """tng_attention_wide (the VAE AttnBlock: one head of width 512, flash-style) against torch; `spread` > 1 makes the
+    key magnitudes grow along the sequence so that rows outgrow the lazy-rescale threshold (O rescale in TMEM)."""
+    Cc = 512
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + Lq)
+    q = torch.randn(B, Lq, Cc, generator=g)
+    k = torch.randn(B, Lq, Cc, generator=g) * torch.linspace(1.0, spread, Lq)[None, :, None]
+    v = torch.randn(B, Lq, Cc, generator=g)
+    qkv = torch.cat([bf(q), bf(k), bf(v)], dim=-1).reshape(B * Lq, 3 * Cc).contiguous().to(cuda)
+    out = torch.zeros(B * Lq, Cc, device=cuda, dtype=torch.bfloat16)
+    L.attention_wide(qkv, qkv, qkv, out, batch=B, L=Lq, dim=Cc, scale=Cc ** -0.5, q_col0=0, k_col0=Cc, v_col0=2 * Cc)
+    s = (bf(q).double() @ bf(k).double().transpose(1, 2)) * Cc ** -0.5
+    ref = (s.softmax(-1) @ bf(v).double()).float()
+    torch.cuda.synchronize()
+    assert rel_err(out.view(B, Lq, Cc).cpu(), ref) < 1e-2      # P and the output are rounded to bf16
+    with pytest.raises(L.TangoB200Error):
+        L.attention_wide(qkv, qkv, qkv, out, batch=B, L=Lq - 64, dim=Cc, scale=1.0)
+
+
 @pytest.mark.parametrize("Cc", [64, 320, 1280])
 def test_layernorm(cuda, Cc):
     rows = 777
