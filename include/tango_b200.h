@@ -107,6 +107,10 @@ typedef struct {
 } tng_gemm_desc;
 
 int tng_conv_gemm(const tng_gemm_desc* d, void* stream);
+/* What tng_conv_gemm would do with this descriptor, without launching: the N tile, the launch mode (1 = one CTA per SM,
+ * 4 = CTA pair on a 256 x 2 block_n tile, 2 / 3 = experiment modes) and the split-K factor. Used by bench.py to label
+ * its per-kernel timings with the instantiation that actually runs. Any output pointer may be NULL. */
+int tng_gemm_plan(const tng_gemm_desc* d, int32_t* block_n, int32_t* mode, int32_t* ksplit);
 
 /* ---------------------------------------------------------------------------------------------------------
  * tng_attention — tcgen05 flash attention, head width 64, fp32 online softmax.

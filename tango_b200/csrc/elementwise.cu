@@ -107,7 +107,7 @@ __device__ __forceinline__ void gn_apply_rows(const void* base, long long idx0, 
   const long long ystep = RL * ystride;
   if (RAW) raw += rl * rstride;
   const long long rstep = RL * rstride;
-#pragma unroll 4
+#pragma unroll 8
   for (int r = rl; r < nrows; r += RL, idx += step, y += ystep) {
     const float4 v = ld_quad<BF>(base, idx);
     float4 o;

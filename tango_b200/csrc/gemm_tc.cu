@@ -816,7 +816,9 @@ static bool is_pow2(long long x) { return x > 0 && (x & (x - 1)) == 0; }
 
 using namespace tng;
 
-extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
+// Everything that is decided before a launch: argument checks, the M tiling, the N tile, split-K, the launch mode and
+// whether the GroupNorm statistics ride in the epilogue. Shared by tng_conv_gemm and tng_gemm_plan.
+static int plan_gemm(const tng_gemm_desc* d, GemmKernelParams& p, int& bn_tile_out, int& cl_out, bool& stats_after_out) {
   if (!d) return set_error(TNG_EINVAL, "null desc");
   if (d->n_aviews < 1 || d->n_aviews > TNG_MAX_AVIEWS) return set_error(TNG_EINVAL, "n_aviews=%d", d->n_aviews);
   if (d->n_groups < 1 || d->n_groups > TNG_MAX_KGROUPS) return set_error(TNG_EINVAL, "n_groups=%d", d->n_groups);
@@ -824,7 +826,6 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   if ((d->ldb > 0 ? d->ldb : d->Ktot) % 8 != 0)
     return set_error(TNG_EINVAL, "B row stride must be a multiple of 8 elements (Ktot=%lld ldb=%lld)", (long long)d->Ktot, (long long)d->ldb);
 
-  GemmKernelParams p;
   memset(&p, 0, sizeof(p));
   p.W = d->W; p.H = d->H; p.NB = d->NB;
   // M tile = bw x bh x bn output pixels (product 128)
@@ -952,6 +953,32 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
                        (d->stats_hw % 32 == 0) && d->act != TNG_ACT_GEGLU && d->act != TNG_ACT_GEGLU_TANH;
     if (fused) { p.col_stats = d->gn_stats; p.stats_hw = d->stats_hw; }
     else stats_after = true;
+  }
+  bn_tile_out = bn_tile;
+  cl_out = cl;
+  stats_after_out = stats_after;
+  return TNG_OK;
+}
+
+extern "C" int tng_gemm_plan(const tng_gemm_desc* d, int32_t* block_n, int32_t* mode, int32_t* ksplit) {
+  GemmKernelParams p;
+  int bn_tile = 0, cl = 1;
+  bool stats_after = false;
+  const int rc = plan_gemm(d, p, bn_tile, cl, stats_after);
+  if (rc != TNG_OK) return rc;
+  if (block_n) *block_n = bn_tile;
+  if (mode) *mode = cl;
+  if (ksplit) *ksplit = p.ksplit;
+  return TNG_OK;
+}
+
+extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
+  GemmKernelParams p;
+  int bn_tile = 0, cl = 1;
+  bool stats_after = false;
+  {
+    const int rc = plan_gemm(d, p, bn_tile, cl, stats_after);
+    if (rc != TNG_OK) return rc;
   }
   // tensor maps
   CUtensorMap am[4];

@@ -24,7 +24,7 @@ SYMBOLS = [
     "tng_groupnorm_stats", "tng_groupnorm_apply", "tng_layernorm", "tng_cast_act", "tng_softmax_rows",
     "tng_transpose_bf16", "tng_sched_step", "tng_timestep_embedding", "tng_linear_f32", "tng_convt_gather",
     "tng_tanh_to_i16", "tng_rmsnorm", "tng_gather_rows", "tng_rel_attention", "tng_stft_frames", "tng_stft_magnitude",
-    "tng_log_clamp", "tng_attention_wide",
+    "tng_log_clamp", "tng_attention_wide", "tng_gemm_plan",
 ]
 
 
@@ -91,6 +91,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     sigs = {
         "tng_conv_gemm": [C.POINTER(GemmDesc), vp],
+        "tng_gemm_plan": [C.POINTER(GemmDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
         "tng_attention": [C.POINTER(AttnDesc), vp],
         "tng_groupnorm_stats": [vp, i32, i64, i64, i64, i64, vp, vp],
         "tng_groupnorm_apply": [vp, i32, i64, vp, vp, i32, i64, vp, i64, i64, i32, vp, vp, f32, i32, vp, i64, i32, vp,
@@ -273,7 +274,11 @@ def conv_gemm(views: Sequence[View], groups: Sequence[tuple], weight: torch.Tens
     if PROF.enabled:
         k_alg = algo_k if algo_k is not None else sum(g[5] for g in groups) * 64
         flops = 2.0 * W * H * NB * weight.shape[0] * k_alg
-        PROF.timed("gemm_tc", flops, 0, lambda: check(lib.tng_conv_gemm(C.byref(d), stream_ptr()), "tng_conv_gemm"))
+        bn, mode, ks = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        check(lib.tng_gemm_plan(C.byref(d), C.byref(bn), C.byref(mode), C.byref(ks)), "tng_gemm_plan")
+        tag = {1: "1cta", 2: "mcast", 3: "pair", 4: "pair2"}.get(mode.value, str(mode.value))
+        fam = f"gemm_tc<{bn.value},{tag}" + (",splitk>" if ks.value > 1 else ">")
+        PROF.timed(fam, flops, 0, lambda: check(lib.tng_conv_gemm(C.byref(d), stream_ptr()), "tng_conv_gemm"))
         return
     check(lib.tng_conv_gemm(C.byref(d), stream_ptr()), "tng_conv_gemm")
 
