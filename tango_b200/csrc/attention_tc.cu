@@ -106,7 +106,6 @@ attention_sub_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_cons
   const int b = blockIdx.z;
   const int n_tiles = (p.Lk + AT_BN - 1) / AT_BN;
   const int n_sub = (p.Lk + SUB - 1) / SUB;
-  pdl_launch_dependents();
 
   if (tid == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -133,7 +132,6 @@ attention_sub_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_cons
   const uint32_t tm_s = tmem_base;
   const uint32_t tm_o = tmem_base + 128;
   const uint32_t tm_p = tmem_base + 192;
-  pdl_wait();   // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
 
   if (warp == 4) {
     // ================================================================= loader / MMA issuer (one elected lane)
@@ -344,14 +342,7 @@ attention_sub_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_cons
               x0 = fmaxf(x0, fmaxf(a01.x, a01.y));
               x1 = fmaxf(x1, fmaxf(a23.x, a23.y));
               pr[i] = ex2_approx(a01.x); pr[i + 1] = ex2_approx(a01.y);
-              if (NSPLIT == 1) {
-                // perf mode: every second pair of exponentials runs on the FMA / ALU pipes (exp2_poly2), which balances
-                // the MUFU unit (8 cycles per warp instruction) against the issue slots of the two resident softmax warps
-                const float2 e23 = exp2_poly2(a23);
-                pr[i + 2] = e23.x; pr[i + 3] = e23.y;
-              } else {
-                pr[i + 2] = ex2_approx(a23.x); pr[i + 3] = ex2_approx(a23.y);
-              }
+              pr[i + 2] = ex2_approx(a23.x); pr[i + 3] = ex2_approx(a23.y);
               l01 = fadd2(l01, make_float2(pr[i], pr[i + 1]));
               l23 = fadd2(l23, make_float2(pr[i + 2], pr[i + 3]));
             }
@@ -493,7 +484,7 @@ static int launch_attn_sub(const tng_attn_desc* d, const CUtensorMap& qm, const 
     attr = true;
   }
   dim3 grid((d->Lq + AT_BM - 1) / AT_BM, d->heads, d->batch);
-  launch_pdl(attention_sub_kernel<NSPLIT, VAR>, grid, dim3(AS_THREADS), Cfg::SMEM_BYTES, st, qm, km, vm, p);
+  attention_sub_kernel<NSPLIT, VAR><<<grid, AS_THREADS, Cfg::SMEM_BYTES, st>>>(qm, km, vm, p);
   count_launch();
   return check_launch("attention_sub");
 }

@@ -63,7 +63,6 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
   const int half = blockIdx.y;
   const int b = blockIdx.z;
   const int n_sub = p.L / AW_SUB;
-  pdl_launch_dependents();
 
   if (tid == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -89,7 +88,6 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
   const uint32_t tm_s = tmem_base;          // 64 columns
   const uint32_t tm_p = tmem_base + 64;     // 32 columns (bf16 pairs)
   const uint32_t tm_o = tmem_base + 128;    // 256 columns
-  pdl_wait();   // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
 
   if (warp == 4) {
     if (lane == 0) {
@@ -312,7 +310,7 @@ extern "C" int tng_attention_wide(const void* q, int64_t ld_q, int32_t q_col0, c
     attr = true;
   }
   dim3 grid(L / AW_BM, AW_D / AW_DV, batch);
-  launch_pdl(attention_wide_kernel, grid, dim3(AW_THREADS), AW_SMEM, reinterpret_cast<cudaStream_t>(stream), qm, km, vm, p);
+  attention_wide_kernel<<<grid, AW_THREADS, AW_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(qm, km, vm, p);
   count_launch();
   return check_launch("attention_wide");
 }

@@ -1,7 +1,6 @@
 // capi.cu — process-wide helpers of libtango_b200.so: error reporting, device query, TMA descriptor encoding.
 #include "tng_internal.h"
 #include <atomic>
-#include <stdlib.h>
 #include <mutex>
 
 namespace tng {
@@ -18,12 +17,6 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-
-bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("TNG_PDL"); on = e ? (atoi(e) != 0) : 1; }
-  return on != 0;
-}
 
 int num_sms() {
   static int sms = 0;

@@ -74,8 +74,6 @@ __device__ __forceinline__ void gn_accum(const void* base, long long idx0, long 
 // Per-(image, channel) sums and sums of squares (fp32 partials over this CTA's rows, fp64 atomics across CTAs).
 __global__ void __launch_bounds__(256) col_stats_kernel(const void* x, int dt, int C, long long ld, long long HW,
                                                          double* stats, int GN_ROWS) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int n = blockIdx.y;
   const long long r0 = static_cast<long long>(blockIdx.x) * GN_ROWS;
   const int Q = C / 4;
@@ -132,8 +130,6 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x0, int dt0, 
                                                         const float* gamma, const float* beta, float eps,
                                                         __nv_bfloat16* y, long long ld_y, int split_off,
                                                         __nv_bfloat16* raw, long long ld_raw, int raw_split_off, int GN_ROWS) {
-  pdl_launch_dependents();
-  pdl_wait();
   // A CTA owns GN_ROWS pixels of image blockIdx.y and the channel slab [c_lo, c_lo + slab) (whole groups, a multiple of
   // 4 channels): it reduces the per-channel accumulators of ITS groups only, so wide concatenated inputs (up to 2560
   // channels) do not make every CTA re-read the statistics of the whole tensor.
@@ -222,8 +218,6 @@ template <int NI, bool RMS>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long long rows, int C, const float* gamma,
                                                          const float* beta, float eps, __nv_bfloat16* y, long long ld_y,
                                                          int split_off, float* yf) {
-  pdl_launch_dependents();
-  pdl_wait();
   const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
   long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -372,8 +366,6 @@ __global__ void __launch_bounds__(128) rel_attention_kernel(const float* qkv, lo
 __global__ void __launch_bounds__(256) cast_act_kernel(const float* x, long long NB, int H, int W, int C, long long ld_x,
                                                         int up, int act, float act_param, __nv_bfloat16* y,
                                                         long long ld_y, int split_off) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int Ho = up ? 2 * H : H, Wo = up ? 2 * W : W;
   const int Q = C / 4;
   const long long total = NB * Ho * Wo * Q;
@@ -398,8 +390,6 @@ __global__ void __launch_bounds__(256) cast_act_kernel(const float* x, long long
 // ------------------------------------------------------------------------------------------------ row softmax
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* x, int L, long long ld_x, float scale,
                                                             __nv_bfloat16* y, long long ld_y, int split_off) {
-  pdl_launch_dependents();
-  pdl_wait();
   __shared__ float red[8];
   __shared__ float bc;
   const long long row = blockIdx.x;
@@ -441,8 +431,6 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* x, int L
 // ------------------------------------------------------------------------------------------------ transpose
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* x, int R, int C, long long ld_x,
                                                               __nv_bfloat16* y, long long ld_y) {
-  pdl_launch_dependents();
-  pdl_wait();
   __shared__ __nv_bfloat16 t[32][33];
   const long long b = blockIdx.z;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -463,8 +451,6 @@ __global__ void __launch_bounds__(256) sched_step_kernel(const float* mo, long l
                                                           const float* sample, const float* noise, const float* coef,
                                                           float* prev, __nv_bfloat16* next_in, long long ld_in,
                                                           int split_off, long long B, int C, long long HW) {
-  pdl_launch_dependents();
-  pdl_wait();
   const float c_x0_s = coef[0], c_x0_m = coef[1], c_prev_x0 = coef[2], c_prev_s = coef[3], c_noise = coef[4];
   const float c_eps_s = coef[5], c_eps_m = coef[6], c_prev_eps = coef[7], clip = coef[8], c_x0_div = coef[9];
   const long long total = B * HW * C;
@@ -549,8 +535,6 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* x, long lo
 __global__ void __launch_bounds__(256) convt_gather_kernel(const float* Y, long long B, long long Lin, int ktaps, int Cout,
                                                             int stride, int pad, long long Lout, const float* bias,
                                                             float* y) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int Q = Cout / 4;
   const long long total = B * Lout * Q;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -573,8 +557,6 @@ __global__ void __launch_bounds__(256) convt_gather_kernel(const float* Y, long 
 }
 
 __global__ void tanh_to_i16_kernel(const float* x, long long n, long long ld_x, float* wf, int16_t* wi) {
-  pdl_launch_dependents();
-  pdl_wait();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float t = tanhf(x[i * ld_x]);
@@ -675,7 +657,7 @@ int launch_col_stats(const void* x, int dt, long long C, long long ld, long long
     return set_error(TNG_EINVAL, "groupnorm_stats: bad shape C=%lld ld=%lld", C, ld);
   const int gn_rows = gn_rows_for(NB, HW);
   dim3 grid((unsigned)((HW + gn_rows - 1) / gn_rows), (unsigned)NB);
-  launch_pdl(col_stats_kernel, grid, dim3(256), 0, st, x, dt, (int)C, ld, HW, col_stats, gn_rows);
+  col_stats_kernel<<<grid, 256, 0, st>>>(x, dt, (int)C, ld, HW, col_stats, gn_rows);
   count_launch();
   return check_launch("col_stats");
 }
@@ -708,9 +690,11 @@ extern "C" int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, cons
   while (tpg * 2 * gps <= 256 && tpg < 32) tpg *= 2;
   const bool silu = act == TNG_ACT_SILU, split = split_off > 0, hasraw = raw_bf16 != nullptr;
 #define TNG_GN_LAUNCH(S, P, R)                                                                                           \
-  launch_pdl(gn_apply_kernel<S, P, R>, grid, dim3(256), 0, ST(stream), x0, dt0, (int)C0, stats0, x1, dt1,               \
-             x1 ? (int)C1 : 0, stats1, HW, groups, tpg, slab, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y),    \
-             ld_y, split_off, reinterpret_cast<__nv_bfloat16*>(raw_bf16), ld_raw, raw_split_off, gn_rows)
+  gn_apply_kernel<S, P, R><<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, stats0, x1, dt1, x1 ? (int)C1 : 0, stats1, HW, \
+                                                          groups, tpg, slab, gamma, beta, eps,                            \
+                                                          reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off,           \
+                                                          reinterpret_cast<__nv_bfloat16*>(raw_bf16), ld_raw,             \
+                                                          raw_split_off, gn_rows)
   if (silu) {
     if (split) { if (hasraw) TNG_GN_LAUNCH(true, true, true); else TNG_GN_LAUNCH(true, true, false); }
     else { if (hasraw) TNG_GN_LAUNCH(true, false, true); else TNG_GN_LAUNCH(true, false, false); }
@@ -729,7 +713,7 @@ extern "C" int tng_layernorm(const float* x, int64_t rows, int64_t C, const floa
   const int wpb = 8;
   const unsigned grid = ln_grid(rows, wpb);
   const int ni = (int)((C / 4 + 31) / 32);
-#define TNG_LN(NI) launch_pdl(layernorm_kernel<NI, false>, dim3(grid), dim3(wpb * 32), 0, ST(stream), x, rows, (int)C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off, static_cast<float*>(nullptr))
+#define TNG_LN(NI) layernorm_kernel<NI, false><<<grid, wpb * 32, 0, ST(stream)>>>(x, rows, (int)C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off, nullptr)
   if (ni <= 1) TNG_LN(1);
   else if (ni <= 2) TNG_LN(2);
   else if (ni <= 3) TNG_LN(3);
@@ -748,7 +732,7 @@ extern "C" int tng_rmsnorm(const float* x, int64_t rows, int64_t C, const float*
   const unsigned grid = ln_grid(rows, wpb);
   const int ni = (int)((C / 4 + 31) / 32);
   const float* beta = nullptr;
-#define TNG_RMS(NI) launch_pdl(layernorm_kernel<NI, true>, dim3(grid), dim3(wpb * 32), 0, ST(stream), x, rows, (int)C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off, y_f32)
+#define TNG_RMS(NI) layernorm_kernel<NI, true><<<grid, wpb * 32, 0, ST(stream)>>>(x, rows, (int)C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off, y_f32)
   if (ni <= 1) TNG_RMS(1);
   else if (ni <= 2) TNG_RMS(2);
   else if (ni <= 3) TNG_RMS(3);
@@ -788,8 +772,8 @@ extern "C" int tng_cast_act(const float* x, int64_t NB, int64_t H, int64_t W, in
                             void* stream) {
   if (!x || !y || C % 4 || ld_x % 4 || ld_y % 4 || split_off % 4) return set_error(TNG_EINVAL, "cast_act: bad shape");
   const long long total = NB * H * W * (upsample2x ? 4 : 1) * (C / 4);
-  launch_pdl(cast_act_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), x, NB, (int)H, (int)W, (int)C, ld_x,
-             upsample2x, act, act_param, reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off);
+  cast_act_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(x, NB, (int)H, (int)W, (int)C, ld_x, upsample2x, act, act_param,
+                                                            reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off);
   count_launch();
   return check_launch("cast_act");
 }
@@ -797,8 +781,8 @@ extern "C" int tng_cast_act(const float* x, int64_t NB, int64_t H, int64_t W, in
 extern "C" int tng_softmax_rows(const float* x, int64_t rows, int64_t L, int64_t ld_x, float scale, void* y,
                                 int64_t ld_y, int32_t split_off, void* stream) {
   if (!x || !y || rows <= 0 || L <= 0) return set_error(TNG_EINVAL, "softmax_rows: bad shape");
-  launch_pdl(softmax_rows_kernel, dim3((unsigned)rows), dim3(256), 0, ST(stream), x, (int)L, ld_x, scale,
-             reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off);
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(x, (int)L, ld_x, scale, reinterpret_cast<__nv_bfloat16*>(y),
+                                                               ld_y, split_off);
   count_launch();
   return check_launch("softmax_rows");
 }
@@ -807,8 +791,8 @@ extern "C" int tng_transpose_bf16(const void* x, int64_t B, int64_t R, int64_t C
                                   void* stream) {
   if (!x || !y) return set_error(TNG_EINVAL, "transpose: null");
   dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)B);
-  launch_pdl(transpose_bf16_kernel, grid, dim3(256), 0, ST(stream), reinterpret_cast<const __nv_bfloat16*>(x), (int)R, (int)C,
-             ld_x, reinterpret_cast<__nv_bfloat16*>(y), ld_y);
+  transpose_bf16_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), (int)R, (int)C, ld_x,
+                                                       reinterpret_cast<__nv_bfloat16*>(y), ld_y);
   count_launch();
   return check_launch("transpose");
 }
@@ -817,8 +801,9 @@ extern "C" int tng_sched_step(const float* model_out, int64_t ld_mo, int32_t cfg
                               const float* noise, const float* coef, float* prev, void* next_in, int64_t ld_in,
                               int32_t split_off, int64_t B, int64_t C, int64_t HW, void* stream) {
   if (!sample || !coef || (!prev && !next_in)) return set_error(TNG_EINVAL, "sched_step: null argument");
-  launch_pdl(sched_step_kernel, dim3(grid_for(B * C * HW)), dim3(256), 0, ST(stream), model_out, ld_mo, cfg, guidance, sample,
-             noise, coef, prev, reinterpret_cast<__nv_bfloat16*>(next_in), ld_in, split_off, B, (int)C, HW);
+  sched_step_kernel<<<grid_for(B * C * HW), 256, 0, ST(stream)>>>(model_out, ld_mo, cfg, guidance, sample, noise, coef, prev,
+                                                                  reinterpret_cast<__nv_bfloat16*>(next_in), ld_in,
+                                                                  split_off, B, (int)C, HW);
   count_launch();
   return check_launch("sched_step");
 }
@@ -843,15 +828,15 @@ extern "C" int tng_linear_f32(const float* x, int64_t M, int64_t K, const float*
 extern "C" int tng_convt_gather(const float* Y, int64_t B, int64_t Lin, int32_t ktaps, int64_t Cout, int32_t stride,
                                 int32_t pad, int64_t Lout, const float* bias, float* y, void* stream) {
   if (!Y || !y || Cout % 4) return set_error(TNG_EINVAL, "convt_gather: bad shape");
-  launch_pdl(convt_gather_kernel, dim3(grid_for(B * Lout * (Cout / 4))), dim3(256), 0, ST(stream), Y, B, Lin, ktaps,
-             (int)Cout, stride, pad, Lout, bias, y);
+  convt_gather_kernel<<<grid_for(B * Lout * (Cout / 4)), 256, 0, ST(stream)>>>(Y, B, Lin, ktaps, (int)Cout, stride, pad, Lout,
+                                                                               bias, y);
   count_launch();
   return check_launch("convt_gather");
 }
 
 extern "C" int tng_tanh_to_i16(const float* x, int64_t n, int64_t ld_x, float* wave_f32, int16_t* wave_i16, void* stream) {
   if (!x) return set_error(TNG_EINVAL, "tanh_to_i16: null");
-  launch_pdl(tanh_to_i16_kernel, dim3(grid_for(n)), dim3(256), 0, ST(stream), x, n, ld_x, wave_f32, wave_i16);
+  tanh_to_i16_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(x, n, ld_x, wave_f32, wave_i16);
   count_launch();
   return check_launch("tanh_to_i16");
 }

@@ -539,7 +539,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -573,9 +572,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const int crank = (CLUSTER > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   if (CLUSTER > 1) cluster_sync_all();  // peer barriers are initialised before any multicast copy / commit targets them
-  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the
-  // tail of the previous kernel; from here on global memory written by it is read (TMA operands, residual) or written.
-  pdl_wait();
 
   // work items: (pair of adjacent M tiles) x N tile; CTA `crank` of the cluster takes M tile 2*mp + crank
   const int m_groups = (p.m_tiles + CLUSTER - 1) / CLUSTER;
@@ -790,15 +786,13 @@ static int launch_gemm_cl(const CUtensorMap* am, const CUtensorMap& bm, const Ge
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CLUSTER;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_wait() in the kernel
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, am[0], am[1], am[2], am[3], bm, p);
   count_launch();
   if (e == cudaSuccess) e = cudaGetLastError();

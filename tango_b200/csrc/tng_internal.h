@@ -21,23 +21,6 @@ int encode_tmap_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t
 // of channels. Used when a GEMM cannot emit the statistics from its epilogue (partial tiles, split-K).
 int launch_col_stats(const void* x, int dt, long long C, long long ld, long long NB, long long HW, double* col_stats,
                      cudaStream_t st);
-// Launch with programmatic stream serialization allowed (see tng_ptx.cuh: pdl_wait / pdl_launch_dependents).
-bool pdl_enabled();   // TNG_PDL=0 turns the attribute off (A/B measurements; bench.py refuses TNG_* variables)
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-}
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(TNG_ECUDA, "%s launch: %s", what, cudaGetErrorString(e));

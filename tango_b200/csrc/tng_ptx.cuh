@@ -138,15 +138,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       : "memory");
 }
 
-// ---------------------------------------------------------------- programmatic dependent launch
-// Every kernel of the path is launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel in the
-// stream (or captured graph) may start its CTAs — barrier init, TMEM allocation, descriptor prefetch, index math — while
-// the tail of the previous one is still running. pdl_launch_dependents() says "my dependents may be scheduled";
-// pdl_wait() blocks until the previous grid has completed and its memory is visible: it must precede the first global
-// access. Both are no-ops for a launch without the attribute.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 // ---------------------------------------------------------------- thread-block clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -310,27 +301,6 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
       : "=l"(reinterpret_cast<unsigned long long&>(d))
       : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
   return d;
-}
-
-// exp2 of two values on the FMA / ALU pipes instead of the MUFU unit: Cody-Waite reduction with the 1.5 * 2^23 magic
-// number (t = x + M rounds x to the nearest integer i in the low mantissa bits), a degree-3 minimax polynomial for 2^f on
-// f = x - i in [-0.5, 0.5] (max relative error 7.5e-5 — probabilities are rounded to bf16, 3.9e-3, right after), and the
-// exponent patched in with one integer shift-add. x is clamped at -125 so the exponent field cannot wrap. 10 issue slots
-// per pair and no MUFU operation; the softmax of the head-width-64 attention is MUFU-bound (1 ex2 per 128 MMA FLOPs).
-__device__ __forceinline__ float2 exp2_poly2(float2 x) {
-  const float2 M = make_float2(12582912.0f, 12582912.0f);
-  x.x = fmaxf(x.x, -125.0f);
-  x.y = fmaxf(x.y, -125.0f);
-  const float2 t = fadd2(x, M);
-  const float2 i = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = ffma2(i, make_float2(-1.0f, -1.0f), x);
-  float2 p = ffma2(make_float2(0.055171236f, 0.055171236f), f, make_float2(0.24261034f, 0.24261034f));
-  p = ffma2(p, f, make_float2(0.69326097f, 0.69326097f));
-  p = ffma2(p, f, make_float2(0.99992812f, 0.99992812f));
-  float2 r;
-  r.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
-  r.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
-  return r;
 }
 
 // ---------------------------------------------------------------- UMMA descriptors
