@@ -319,3 +319,34 @@ def test_tiny_unet_music_golden():
     out = ounet.unet_forward(sd, cfg, tt("sample"), torch.tensor(int(gd["t"])), tt("ehs"), tt("mask"),
                              extra_streams=((tt("beat"), tt("bmask")), (tt("chord"), tt("cmask"))))
     assert np.abs(out.numpy() - gd["out"]).max() < 5e-5
+
+
+def test_config1_artefact_pins_the_oracle_at_full_size():
+    """tests/golden/config1.npz (the reference's own config-1 run: full 866 M-parameter UNet, 1 prompt, CFG 3, 10 steps at
+    256 x 16, then VAE + HiFi-GAN): the oracle reproduces (a) the first step of both loops — the per-step latent norms the
+    reference loop recorded — and (b) mel and int16 waveform from the reference's final DDIM latents. (The full 10-step
+    oracle loops are asserted against the reference inside oracle/make_golden_config1.py, ~3 min; here one CFG forward
+    per scheduler keeps the CPU suite short.)"""
+    from oracle import make_golden_config1 as c1
+    gd = np.load(os.path.join(GOLD, "config1.npz"))
+    assert gd["timesteps_ddpm"].tolist() == list(range(900, -1, -100))
+    assert gd["timesteps_ddim"].tolist() == list(range(901, 0, -100))
+    cfg, embeds, mask, lat0, noises = c1.inputs()
+    sd = synth.synth_state_dict(synth.unet_param_shapes(cfg), seed=c1.SEEDS["weights"])
+    for name, sch in (("ddpm", osched.OracleDDPM(**osched.SD21_CONFIG)), ("ddim", osched.OracleDDIM(**osched.SD21_CONFIG))):
+        sch.set_timesteps(c1.STEPS)
+        t = sch.timesteps[0]
+        x = torch.cat([lat0 * sch.init_noise_sigma] * 2)
+        pred = ounet.unet_forward(sd, cfg, x, t, embeds, mask)
+        u, c = pred.chunk(2)
+        pred = u + c1.GUIDANCE * (c - u)
+        lat1 = sch.step(pred, t, lat0, noises[0]) if name == "ddpm" else sch.step(pred, t, lat0)
+        want = float(gd[f"step_norms_{name}"][0])
+        assert abs(float(lat1.norm()) - want) / want < 2e-6, name
+    del sd
+    vsd = synth.synth_state_dict(synth.vae_decoder_param_shapes(), seed=c1.SEEDS["weights"])
+    lat = torch.from_numpy(gd["latents_ddim"])
+    mel = ovae.decode_first_stage(vsd, lat, synth.VAE_CONFIG["scale_factor"])
+    _, i16 = ohifi.decode_to_waveform(vsd, mel)
+    assert float((mel - torch.from_numpy(gd["mel"])).abs().max()) < 1e-4
+    assert int(np.abs(np.asarray(i16).astype(np.int32) - gd["wave_i16"].astype(np.int32)).max()) <= 1
