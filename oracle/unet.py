@@ -70,24 +70,24 @@ def upsample2d(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
 
 def attention(sd: SD, p: str, x: torch.Tensor, ctx: Optional[torch.Tensor], heads: int,
               bias: Optional[torch.Tensor]) -> torch.Tensor:
-    """D/models/attention_processor.py:263-299 (AttnProcessor: baddbmm + softmax + bmm; the fp32 result equals
-    AttnProcessor2_0's SDPA, :500-540). bias: additive [B, 1, Lk] or None."""
+    """D/models/attention_processor.py:500-540 — AttnProcessor2_0, the processor the reference selects on any torch that
+    has F.scaled_dot_product_attention (attention_processor.py:104-111): q / k / v projections, heads split, SDPA with
+    the additive mask bias expanded over heads and queries, out projection. (AttnProcessor's baddbmm + softmax + bmm,
+    :263-299, gives the same fp32 result to round-off; SDPA is what actually runs — and what the CPU baseline of bench.py
+    should time: it does not materialise the [B, heads, Lq, Lk] score tensor.) bias: additive [B, 1, Lk] or None."""
     B, Lq, Cc = x.shape
     src = x if ctx is None else ctx
     q = F.linear(x, sd[p + ".to_q.weight"])
     k = F.linear(src, sd[p + ".to_k.weight"])
     v = F.linear(src, sd[p + ".to_v.weight"])
     d = Cc // heads
-    scale = d ** -0.5
     Lk = src.shape[1]
     q = q.view(B, Lq, heads, d).transpose(1, 2)
     k = k.view(B, Lk, heads, d).transpose(1, 2)
     v = v.view(B, Lk, heads, d).transpose(1, 2)
-    s = torch.matmul(q, k.transpose(-1, -2)) * scale
-    if bias is not None:
-        s = s + bias[:, None, :, :]
-    pr = s.softmax(dim=-1)
-    o = torch.matmul(pr, v).transpose(1, 2).reshape(B, Lq, Cc)
+    mask = None if bias is None else bias[:, None, :, :].expand(B, heads, Lq, Lk)
+    o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=0.0, is_causal=False)
+    o = o.transpose(1, 2).reshape(B, Lq, Cc)
     return _lin(sd, p + ".to_out.0", o)
 
 
