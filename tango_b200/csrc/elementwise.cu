@@ -653,7 +653,7 @@ using namespace tng;
 namespace tng {
 int launch_col_stats(const void* x, int dt, long long C, long long ld, long long NB, long long HW, double* col_stats,
                      cudaStream_t st) {
-  if (!x || !col_stats || C <= 0 || C % 4 || ld % 4 || NB <= 0 || HW <= 0 || (reinterpret_cast<uintptr_t>(x) & 15))
+  if (!x || !col_stats || C <= 0 || C % 4 || ld % 4 || NB <= 0 || HW <= 0 || (reinterpret_cast<uintptr_t>(x) & 7))
     return set_error(TNG_EINVAL, "groupnorm_stats: bad shape C=%lld ld=%lld", C, ld);
   const int gn_rows = gn_rows_for(NB, HW);
   dim3 grid((unsigned)((HW + gn_rows - 1) / gn_rows), (unsigned)NB);

@@ -292,31 +292,31 @@ __device__ __forceinline__ void epi_chunk_full(const GemmKernelParams& p, const 
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(op + i * os) = a[i];
-    if (p.col_stats) {
-      // Column sums of this warp's 32 rows x 32 columns (all rows belong to image stats_img): 8 rows in registers,
-      // then across the four row-lanes (lane bits 3 and 4); lanes 0..7 hold the totals of their 4 columns and add
-      // them to the fp64 per-(image, channel) accumulators — fp32 partials over 32 values, fp64 across tiles.
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  }
+  if (p.col_stats) {
+    // Column sums of this warp's 32 rows x 32 columns (all rows belong to image stats_img): 8 rows in registers,
+    // then across the four row-lanes (lane bits 3 and 4); lanes 0..7 hold the totals of their 4 columns and add
+    // them to the fp64 per-(image, channel) accumulators — fp32 partials over 32 values, fp64 across tiles.
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s0 += a[i].x; s1 += a[i].y; s2 += a[i].z; s3 += a[i].w;
-        q0 = fmaf(a[i].x, a[i].x, q0); q1 = fmaf(a[i].y, a[i].y, q1);
-        q2 = fmaf(a[i].z, a[i].z, q2); q3 = fmaf(a[i].w, a[i].w, q3);
-      }
+    for (int i = 0; i < 8; ++i) {
+      s0 += a[i].x; s1 += a[i].y; s2 += a[i].z; s3 += a[i].w;
+      q0 = fmaf(a[i].x, a[i].x, q0); q1 = fmaf(a[i].y, a[i].y, q1);
+      q2 = fmaf(a[i].z, a[i].z, q2); q3 = fmaf(a[i].w, a[i].w, q3);
+    }
 #pragma unroll
-      for (int o = 8; o <= 16; o <<= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
-        q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-        q2 += __shfl_xor_sync(0xffffffffu, q2, o); q3 += __shfl_xor_sync(0xffffffffu, q3, o);
-      }
-      if (rsub == 0) {
-        double* sp = p.col_stats + (stats_img * p.Ncols + col) * 2;
-        atomicAdd(sp + 0, static_cast<double>(s0)); atomicAdd(sp + 1, static_cast<double>(q0));
-        atomicAdd(sp + 2, static_cast<double>(s1)); atomicAdd(sp + 3, static_cast<double>(q1));
-        atomicAdd(sp + 4, static_cast<double>(s2)); atomicAdd(sp + 5, static_cast<double>(q2));
-        atomicAdd(sp + 6, static_cast<double>(s3)); atomicAdd(sp + 7, static_cast<double>(q3));
-      }
+    for (int o = 8; o <= 16; o <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+      q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+      q2 += __shfl_xor_sync(0xffffffffu, q2, o); q3 += __shfl_xor_sync(0xffffffffu, q3, o);
+    }
+    if (rsub == 0) {
+      double* sp = p.col_stats + (stats_img * p.Ncols + col) * 2;
+      atomicAdd(sp + 0, static_cast<double>(s0)); atomicAdd(sp + 1, static_cast<double>(q0));
+      atomicAdd(sp + 2, static_cast<double>(s1)); atomicAdd(sp + 3, static_cast<double>(q1));
+      atomicAdd(sp + 4, static_cast<double>(s2)); atomicAdd(sp + 5, static_cast<double>(q2));
+      atomicAdd(sp + 6, static_cast<double>(s3)); atomicAdd(sp + 7, static_cast<double>(q3));
     }
   }
   if (BF16) {
@@ -918,8 +918,10 @@ static int plan_gemm(const tng_gemm_desc* d, GemmKernelParams& p, int& bn_tile_o
   p.fast_epi = (vec && d->Ncols % 4 == 0) ? 1 : 0;
   if ((d->act == TNG_ACT_GEGLU || d->act == TNG_ACT_GEGLU_TANH) && !vec) return set_error(TNG_EINVAL, "GEGLU epilogue needs 16-byte aligned output");
   if (d->gn_stats) {
-    if (!d->out_f32 || d->stats_hw <= 0 || (static_cast<long long>(d->W) * d->H * d->NB) % d->stats_hw != 0)
-      return set_error(TNG_EINVAL, "gn_stats needs an fp32 output whose rows are whole images of stats_hw pixels");
+    if (d->stats_hw <= 0 || (static_cast<long long>(d->W) * d->H * d->NB) % d->stats_hw != 0)
+      return set_error(TNG_EINVAL, "gn_stats: the output rows must be whole images of stats_hw pixels");
+    if (!d->out_f32 && (d->split_off > 0 || d->act != TNG_ACT_NONE))
+      return set_error(TNG_EINVAL, "gn_stats without an fp32 output needs a plain bf16 output (no activation, no hi/lo split)");
   }
 
   // Launch mode. 1 = one CTA per SM; 4 = CTA pair (tcgen05 cta_group::2) on a 256 x (2 x bn_tile) output tile: each SM
@@ -1016,7 +1018,9 @@ extern "C" int tng_conv_gemm(const tng_gemm_desc* d, void* stream) {
   }
   if (rc == TNG_OK && stats_after) {
     const long long rows = static_cast<long long>(d->W) * d->H * d->NB;
-    rc = launch_col_stats(d->out_f32, TNG_DT_F32, d->Ncols, d->ld_f32, rows / d->stats_hw, d->stats_hw, d->gn_stats, st);
+    // (from the stored output: fp32 when there is one, else the bf16 output — the rounded values the consumer reads)
+    if (d->out_f32) rc = launch_col_stats(d->out_f32, TNG_DT_F32, d->Ncols, d->ld_f32, rows / d->stats_hw, d->stats_hw, d->gn_stats, st);
+    else rc = launch_col_stats(d->out_bf16, TNG_DT_BF16, d->Ncols, d->ld_bf16, rows / d->stats_hw, d->stats_hw, d->gn_stats, st);
   }
   return rc;
 }

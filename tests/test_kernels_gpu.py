@@ -340,6 +340,15 @@ def test_conv_gemm_emits_groupnorm_statistics(cuda, shape):
     run_conv(pc, bf(x).to(cuda), NB, H, W, res=res if taps == 1 else None, out_f32=out, gn_stats=st, stats_hw=H * W)
     torch.cuda.synchronize()
     assert rel_err(st[..., 0], 2 * o.sum(1)) < 1e-6
+    # bf16-only output (conv1 of a resnet in perf mode): the statistics are those of the fp32 epilogue values when they
+    # ride in the epilogue, of the stored bf16 values when the follow-up pass computes them — either way within bf16
+    # rounding of the fp32 sums
+    ob = torch.zeros(NB * H * W, Cout, device=cuda, dtype=torch.bfloat16)
+    st2 = torch.zeros(NB, Cout, 2, device=cuda, dtype=torch.float64)
+    run_conv(pc, bf(x).to(cuda), NB, H, W, res=res if taps == 1 else None, out_bf16=ob, gn_stats=st2, stats_hw=H * W)
+    torch.cuda.synchronize()
+    assert rel_err(ob, out) < 5e-3
+    assert rel_err(st2[..., 1], (o * o).sum(1)) < 5e-3 and rel_err(st2[..., 0], o.sum(1)) < 2e-2
 
 
 @pytest.mark.parametrize("B,Lq,spread", [(2, 256, 1.0), (1, 1024, 1.0), (2, 384, 6.0)])
