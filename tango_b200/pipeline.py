@@ -343,7 +343,10 @@ class AudioDiffusion:
             # exactly 0 in fp32), so the result is unchanged while real traffic needs one graph per bucket, not per length
             pad = self.LK_BUCKET - prompt_embeds.shape[1] % self.LK_BUCKET
             prompt_embeds = torch.nn.functional.pad(prompt_embeds, (0, 0, 0, pad))
-            boolean_prompt_mask = torch.nn.functional.pad(boolean_prompt_mask.to(torch.bool), (0, pad), value=False)
+            if boolean_prompt_mask.dtype is torch.bool:
+                boolean_prompt_mask = torch.nn.functional.pad(boolean_prompt_mask, (0, pad), value=False)
+            else:   # any other dtype is already an additive bias (unet_2d_condition.py:573-578): padded keys get -10000
+                boolean_prompt_mask = torch.nn.functional.pad(boolean_prompt_mask, (0, pad), value=-10000.0)
         unet.set_conditioning(prompt_embeds, boolean_prompt_mask, extra_streams=extra_streams)
         tkey = (unet.pack_generation, str(device)) + tuple(sch._t_list)   # packed weights are rebuilt on (re)load
         if self._temb_cache.get("key") != tkey:   # batch- and data-independent: reuse across calls with the same grid
