@@ -537,7 +537,7 @@ def text_encoder_leg(args, dev):
     torch.cuda.empty_cache()
     return {"model": ("flan-t5-large" if args.unet == "base" else "flan-t5-xl") + " encoder, seeded random weights",
             "prompts": args.batch, "tokens": args.tokens, "ms": ms, "tflops": flops / (ms / 1e3) / 1e12,
-            "note": "eager launches (not graph-captured); outside the timed metric"}
+            "note": "one CUDA-graph replay per call; outside the timed metric"}
 
 
 def cpu_baseline(args):

@@ -76,6 +76,8 @@ class T5EncoderModel:
         self._sd: Optional[Dict[str, torch.Tensor]] = None
         self._packed = False
         self._relbias = {}
+        self._graphs = {}
+        self.use_cuda_graph = True      # one graph per (batch, padded length); off under the CPU orchestration tests
 
     # ----------------------------------------------------------------------------------------- transformers-style API
     @classmethod
@@ -156,6 +158,7 @@ class T5EncoderModel:
             b.ff2 = PackedConv(sd[p + "1.DenseReluDense.wo.weight"], None, split=sp, device=dev)
             self.blocks.append(b)
         self._relbias = {}
+        self._graphs = {}
         self._packed = True
 
     def _relbias_for(self, L_: int) -> torch.Tensor:
@@ -181,30 +184,54 @@ class T5EncoderModel:
             raise IndexError(f"token id out of range [0, {cfg['vocab_size']}): min {lo}, max {hi}")
         d, H, ff = cfg["d_model"], cfg["num_heads"], cfg["d_ff"]
         inner, rows, eps = H * 64, B * Lt, float(cfg["layer_norm_epsilon"])
-        x = torch.empty(rows, d, device=dev, dtype=torch.float32)
-        L.gather_rows(self.emb, ids.view(-1), x)
-        kbias = None
-        if attention_mask is not None:
+        key = (B, Lt, attention_mask is not None)
+        st = self._graphs.get(key)
+        if st is None:
+            # persistent operands: the ~170 launches of the stack are captured once per (batch, length) into a CUDA graph
+            st = SimpleNamespace(
+                ids=torch.zeros(rows, device=dev, dtype=torch.int64),
+                kbias=torch.zeros(B, Lt, device=dev, dtype=torch.float32) if attention_mask is not None else None,
+                x=torch.empty(rows, d, device=dev, dtype=torch.float32),
+                n=torch.empty(rows, s * d, device=dev, dtype=torch.bfloat16),
+                qkv=torch.empty(rows, 3 * inner, device=dev, dtype=torch.float32),
+                ctx=torch.empty(rows, s * inner, device=dev, dtype=torch.bfloat16),
+                hff=torch.empty(rows, s * ff, device=dev, dtype=torch.bfloat16),
+                out=torch.empty(rows, d, device=dev, dtype=torch.float32), graph=None)
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = st
+        st.ids.copy_(ids.view(-1))
+        if st.kbias is not None:
             # get_extended_attention_mask: (1 - mask) * finfo.min, added to the position bias
-            kbias = ((1.0 - attention_mask.to(dev).float()) * torch.finfo(torch.float32).min).contiguous()
+            st.kbias.copy_((1.0 - attention_mask.to(dev).float()) * torch.finfo(torch.float32).min)
         relbias = self._relbias_for(Lt)
-        n = torch.empty(rows, s * d, device=dev, dtype=torch.bfloat16)
-        qkv = torch.empty(rows, 3 * inner, device=dev, dtype=torch.float32)
-        ctx = torch.empty(rows, s * inner, device=dev, dtype=torch.bfloat16)
-        hff = torch.empty(rows, s * ff, device=dev, dtype=torch.bfloat16)
         so_d, so_i = (d if self.split else 0), (inner if self.split else 0)
-        for b in self.blocks:
-            L.rmsnorm(x, b.ln0, eps, n, split_off=so_d)
-            run_linear(b.qkv, n, out_f32=qkv)
-            L.rel_attention(qkv, relbias, kbias, ctx, batch=B, heads=H, L=Lt, q_col0=0, k_col0=inner, v_col0=2 * inner,
-                            split_off=so_i)
-            run_linear(b.o, ctx, res=x, out_f32=x)
-            L.rmsnorm(x, b.ln1, eps, n, split_off=so_d)
-            run_linear(b.ff1, n, out_bf16=hff)
-            run_linear(b.ff2, hff, res=x, out_f32=x)
-        # final T5LayerNorm in fp32: it is the tensor handed to the UNet's cross-attention K/V projections
-        out = torch.empty(rows, d, device=dev, dtype=torch.float32)
-        L.rmsnorm(x, self.final_ln, eps, y_f32=out)
-        return T5Output(out.view(B, Lt, d))
+
+        def run():
+            x, n, qkv, ctx, hff = st.x, st.n, st.qkv, st.ctx, st.hff
+            L.gather_rows(self.emb, st.ids, x)
+            for b in self.blocks:
+                L.rmsnorm(x, b.ln0, eps, n, split_off=so_d)
+                run_linear(b.qkv, n, out_f32=qkv)
+                L.rel_attention(qkv, relbias, st.kbias, ctx, batch=B, heads=H, L=Lt, q_col0=0, k_col0=inner,
+                                v_col0=2 * inner, split_off=so_i)
+                run_linear(b.o, ctx, res=x, out_f32=x)
+                L.rmsnorm(x, b.ln1, eps, n, split_off=so_d)
+                run_linear(b.ff1, n, out_bf16=hff)
+                run_linear(b.ff2, hff, res=x, out_f32=x)
+            # final T5LayerNorm in fp32: it is the tensor handed to the UNet's cross-attention K/V projections
+            L.rmsnorm(x, self.final_ln, eps, y_f32=st.out)
+
+        if not (self.use_cuda_graph and dev.type == "cuda"):
+            run()
+        else:
+            if st.graph is None:
+                run()                                  # warm-up: kernel attributes
+                torch.cuda.synchronize()
+                st.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(st.graph):
+                    run()
+            st.graph.replay()
+        return T5Output(st.out.view(B, Lt, d).clone())
 
     __call__ = forward
