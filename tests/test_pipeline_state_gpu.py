@@ -183,3 +183,36 @@ def test_two_rank_nccl_run_equals_one_rank_run(cuda):
         assert len(res[r]) == 5
         for got, w in zip(res[r], want):
             assert np.abs(np.asarray(got, dtype=np.int32) - w.astype(np.int32)).max() <= 2
+
+
+def test_cli_two_ranks_reproduces_single_rank_wavs(cuda, tmp_path):
+    """`torchrun --nproc-per-node 2 -m tango_b200.cli --seed S` writes the wav files of the one-GPU run with the same
+    seed (every chunk of prompts is split over the ranks, each rank keeps its rows of the shared noise stream) - needs
+    2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+    import subprocess
+    import sys
+    import wave
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    man = tmp_path / "prompts.json"
+    man.write_text("\n".join(json.dumps({"captions": c}) for c in ["a dog barking", "rain", "church bells", "a train", "wind"]))
+    common = ["--checkpoint", "synthetic:tiny", "--test_file", str(man), "--num_steps", "3", "--batch_size", "4",
+              "--latent_h", "32", "--seed", "11", "--precision", "split"]
+    env = dict(os.environ, PYTHONPATH=root)
+    r1 = subprocess.run([sys.executable, "-m", "tango_b200.cli", *common, "--output_root", str(tmp_path / "one"), "--exp_id", "a"],
+                        cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0, r1.stderr[-2000:]
+    r2 = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                         "127.0.0.1", "--master-port", str(_free_port()), "-m", "tango_b200.cli", *common, "--output_root",
+                         str(tmp_path / "two"), "--exp_id", "a"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    for j in range(5):
+        frames = []
+        for d in ("one", "two"):
+            with wave.open(str(tmp_path / d / "a_steps_3_guidance_3" / f"output_{j}.wav")) as w:
+                frames.append(np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.int32))
+        assert frames[0].shape == frames[1].shape and np.abs(frames[0] - frames[1]).max() <= 2, j
+    line = (tmp_path / "two" / "tango_checkpoint_summary.jsonl").read_text().strip()
+    assert json.loads(line)["n_gpus"] == 2
