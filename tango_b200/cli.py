@@ -85,7 +85,7 @@ def build_tango(checkpoint: str, device: str, precision: str, scheduler: str):
     t = Tango(checkpoint, device, precision=precision)
     if scheduler == "ddim":
         from .schedulers import DDIMScheduler
-        t.scheduler = DDIMScheduler.from_pretrained(None)
+        t.scheduler = DDIMScheduler.from_pretrained(t.scheduler_name, subfolder="scheduler")   # same scheduler_config.json
     return t
 
 

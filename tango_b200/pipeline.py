@@ -459,7 +459,8 @@ class Tango:
         self.vae.eval()
         self.stft.eval()
         self.model.eval()
-        self.scheduler = DDPMScheduler.from_pretrained(main_config.get("scheduler_name"), subfolder="scheduler")
+        self.scheduler_name = main_config.get("scheduler_name")
+        self.scheduler = DDPMScheduler.from_pretrained(self.scheduler_name, subfolder="scheduler")
 
     @classmethod
     def from_synthetic(cls, unet_config: Optional[dict] = None, device="cuda:0", precision: str = "bf16", seed: int = 0,
