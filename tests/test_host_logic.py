@@ -259,3 +259,55 @@ def test_product_scheduler_tables_meet_reference_loop_constants():
             noise = torch.randn(res.shape, generator=g) if int(t) > 0 else None
             x = emulate_step(tab[i], res, x, noise)
         assert abs(x.abs().sum().item() - es) < 1e-2 and abs(x.abs().mean().item() - em) < 1e-3
+
+
+def test_generate_for_batch_chunking_sharding_and_generator_routing(monkeypatch):
+    """Host logic of Tango.generate_for_batch (tango.py:51-64 + the shard / seed contract of SURVEY.md section 8e) with
+    the model and decoder stubbed: chunks of batch_size, contiguous split of every chunk over the ranks, the row window
+    handed to the noise draws, per-sample generator lists sliced per chunk and rank, empty shards advancing the RNG."""
+    import numpy as np
+    from tango_b200 import parallel
+    from tango_b200.pipeline import Tango
+
+    calls, advanced = [], []
+
+    class _Model:
+        use_cuda_graph = False
+
+        def inference(self, prompts, scheduler, steps, guidance, samples, disable_progress=True, generator=None,
+                      noise_rows=None, **kw):
+            calls.append((list(prompts), samples, generator, noise_rows))
+            return torch.zeros(len(prompts) * samples, 8, 4, 4)
+
+        def advance_rng(self, total, scheduler, steps, generator, latent_shape):
+            advanced.append((total, generator))
+
+    t = Tango.__new__(Tango)
+    t.model, t.scheduler, t.device = _Model(), object(), torch.device("cpu")
+    ids = iter(range(10 ** 6))
+    t._decode = lambda lat: np.stack([np.full(3, next(ids), dtype=np.int16) for _ in range(lat.shape[0])])
+    prompts = [f"p{i}" for i in range(5)]
+
+    # single process: chunks of 2, 2, 1; samples = 2 -> groups of 2 waveforms per prompt, generator passed through
+    out = t.generate_for_batch(prompts, steps=1, guidance=3, samples=2, batch_size=2, generator="G")
+    assert [c[0] for c in calls] == [["p0", "p1"], ["p2", "p3"], ["p4"]] and all(c[2] == "G" and c[3] is None for c in calls)
+    assert len(out) == 5 and all(len(o) == 2 for o in out)
+    # per-sample generator list: sliced per chunk (2 prompts x 2 samples = 4 generators per chunk)
+    calls.clear()
+    gens = [f"g{i}" for i in range(10)]
+    t.generate_for_batch(prompts, steps=1, guidance=3, samples=2, batch_size=2, generator=gens)
+    assert [c[2] for c in calls] == [gens[0:4], gens[4:8], gens[8:10]]
+    with pytest.raises(ValueError):
+        t.generate_for_batch(prompts, steps=1, guidance=3, samples=2, batch_size=2, generator=gens[:7])
+    # world of 2, rank 1: chunk [p0..p3] -> rows 2..3 of 4; chunk [p4] -> empty shard, RNG advanced instead
+    calls.clear()
+    monkeypatch.setattr(parallel, "world_size", lambda: 2)
+    monkeypatch.setattr(parallel, "rank", lambda: 1)
+    monkeypatch.setattr(parallel, "allgather_waves", lambda w, dev=None: w)
+    out = t.generate_for_batch(prompts, steps=7, guidance=3, samples=1, batch_size=4, generator="G", shard=True)
+    assert calls == [(["p2", "p3"], 1, "G", (2, 4, 4))]
+    assert advanced == [(1, "G")] and len(out) == 2
+    # shard=False ignores the process group
+    calls.clear()
+    t.generate_for_batch(prompts[:2], steps=1, guidance=3, batch_size=8)
+    assert calls[0][0] == ["p0", "p1"] and calls[0][3] is None
