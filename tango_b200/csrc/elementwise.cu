@@ -101,25 +101,44 @@ template <bool BF, bool SILU, bool SPLIT, bool RAW>
 __device__ __forceinline__ void gn_apply_rows(const void* base, long long idx0, long long stride, int rl, int nrows, int RL,
                                               const float* sc, const float* sh, __nv_bfloat16* y, long long ystride,
                                               int split_off, __nv_bfloat16* raw, long long rstride, int raw_split_off) {
+  // Rows rl, rl + RL, ... of this thread's 4 channels, in batches of UN: all loads of a batch are issued before the first
+  // store (the compiler will not move a load above a store that may alias it, and one 16-byte load in flight per thread
+  // leaves the kernel latency-bound), the last batch is predicated.
+  constexpr int UN = 8;
+  const int n = (nrows - rl + RL - 1) / RL;   // rows of this thread
+  if (n <= 0) return;
+  const int nb = (n + UN - 1) / UN;
+  const int per = (n + nb - 1) / nb;          // balanced batches of at most UN rows
   long long idx = idx0 + rl * stride;
   const long long step = RL * stride;
   y += rl * ystride;
   const long long ystep = RL * ystride;
   if (RAW) raw += rl * rstride;
   const long long rstep = RL * rstride;
-#pragma unroll 8
-  for (int r = rl; r < nrows; r += RL, idx += step, y += ystep) {
-    const float4 v = ld_quad<BF>(base, idx);
-    float4 o;
-    o.x = fmaf(v.x, sc[0], sh[0]); o.y = fmaf(v.y, sc[1], sh[1]); o.z = fmaf(v.z, sc[2], sh[2]); o.w = fmaf(v.w, sc[3], sh[3]);
-    if (SILU) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
-    store4_bf16(y, o);
-    if (SPLIT) store4_bf16(y + split_off, make_float4(bf16_lo(o.x), bf16_lo(o.y), bf16_lo(o.z), bf16_lo(o.w)));
-    if (RAW) {
-      store4_bf16(raw, v);
-      if (SPLIT) store4_bf16(raw + raw_split_off, make_float4(bf16_lo(v.x), bf16_lo(v.y), bf16_lo(v.z), bf16_lo(v.w)));
-      raw += rstep;
+#pragma unroll 1
+  for (int k0 = 0; k0 < n; k0 += per, idx += per * step, y += per * ystep) {
+    const int cnt = (n - k0) < per ? (n - k0) : per;
+    float4 v[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+      v[u] = (u < cnt) ? ld_quad<BF>(base, idx + u * step) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (u >= cnt) break;
+      float4 o;
+      o.x = fmaf(v[u].x, sc[0], sh[0]); o.y = fmaf(v[u].y, sc[1], sh[1]);
+      o.z = fmaf(v[u].z, sc[2], sh[2]); o.w = fmaf(v[u].w, sc[3], sh[3]);
+      if (SILU) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+      __nv_bfloat16* yp = y + u * ystep;
+      store4_bf16(yp, o);
+      if (SPLIT) store4_bf16(yp + split_off, make_float4(bf16_lo(o.x), bf16_lo(o.y), bf16_lo(o.z), bf16_lo(o.w)));
+      if (RAW) {
+        __nv_bfloat16* rp = raw + u * rstep;
+        store4_bf16(rp, v[u]);
+        if (SPLIT) store4_bf16(rp + raw_split_off, make_float4(bf16_lo(v[u].x), bf16_lo(v[u].y), bf16_lo(v[u].z), bf16_lo(v[u].w)));
+      }
     }
+    if (RAW) raw += per * rstep;
   }
 }
 
@@ -369,21 +388,38 @@ __global__ void __launch_bounds__(256) cast_act_kernel(const float* x, long long
   const int Ho = up ? 2 * H : H, Wo = up ? 2 * W : W;
   const int Q = C / 4;
   const long long total = NB * Ho * Wo * Q;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int q = static_cast<int>(i % Q);
-    const long long orow = i / Q;
-    long long irow = orow;
-    if (up) {
-      const int wo = static_cast<int>(orow % Wo);
-      const int ho = static_cast<int>((orow / Wo) % Ho);
-      const long long n = orow / (static_cast<long long>(Wo) * Ho);
-      irow = (n * H + (ho >> 1)) * W + (wo >> 1);
+  const long long gstride = static_cast<long long>(gridDim.x) * blockDim.x;
+  constexpr int UN = 4;   // loads of UN grid-stride iterations are issued before the first store (see gn_apply_rows)
+  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < total; i0 += UN * gstride) {
+    float4 v[UN];
+    long long oidx[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long i = i0 + u * gstride;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      oidx[u] = -1;
+      if (i < total) {
+        const int q = static_cast<int>(i % Q);
+        const long long orow = i / Q;
+        long long irow = orow;
+        if (up) {
+          const int wo = static_cast<int>(orow % Wo);
+          const int ho = static_cast<int>((orow / Wo) % Ho);
+          const long long n = orow / (static_cast<long long>(Wo) * Ho);
+          irow = (n * H + (ho >> 1)) * W + (wo >> 1);
+        }
+        v[u] = *reinterpret_cast<const float4*>(x + irow * ld_x + q * 4);
+        oidx[u] = orow * ld_y + q * 4;
+      }
     }
-    float4 v = *reinterpret_cast<const float4*>(x + irow * ld_x + q * 4);
-    v.x = act_f(v.x, act, act_param); v.y = act_f(v.y, act, act_param);
-    v.z = act_f(v.z, act, act_param); v.w = act_f(v.w, act, act_param);
-    store4_split(y + orow * ld_y + q * 4, v, split_off);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (oidx[u] < 0) continue;
+      float4 w = v[u];
+      w.x = act_f(w.x, act, act_param); w.y = act_f(w.y, act, act_param);
+      w.z = act_f(w.z, act, act_param); w.w = act_f(w.w, act, act_param);
+      store4_split(y + oidx[u], w, split_off);
+    }
   }
 }
 
@@ -629,6 +665,16 @@ static inline int gn_rows_for(long long NB, long long HW) {
   return static_cast<int>(rows);
 }
 
+// pixels per gn_apply CTA so that blocks * ceil(HW / rows) CTAs fit one wave of per_sm resident CTAs per SM
+static inline int gn_rows_one_wave(long long blocks, long long HW, int per_sm) {
+  long long gx = (static_cast<long long>(per_sm) * num_sms()) / (blocks > 0 ? blocks : 1);
+  if (gx < 1) gx = 1;
+  long long rows = (HW + gx - 1) / gx;
+  if (rows < 8) rows = 8;
+  if (rows > HW) rows = HW;
+  return static_cast<int>(rows);
+}
+
 // LayerNorm grid: one warp per row up to 4 CTAs of `wpb` warps per SM, then the warps stride over the rows
 static inline unsigned ln_grid(long long rows, int wpb) {
   long long g = (rows + wpb - 1) / wpb;
@@ -684,17 +730,28 @@ extern "C" int tng_groupnorm_apply(const void* x0, int32_t dt0, int64_t C0, cons
   while (gps * 2 * cpg <= 320 && groups % (gps * 2) == 0) gps *= 2;
   if ((gps * cpg) % 4 != 0 || groups % gps != 0) { gps = groups; }   // fall back: one slab = all channels
   const int slab = gps * cpg, nslabs = groups / gps;
-  const int gn_rows = gn_rows_for(NB * nslabs, HW);
-  dim3 grid((unsigned)((HW + gn_rows - 1) / gn_rows), (unsigned)NB, (unsigned)nslabs);
   int tpg = 1;
   while (tpg * 2 * gps <= 256 && tpg < 32) tpg *= 2;
   const bool silu = act == TNG_ACT_SILU, split = split_off > 0, hasraw = raw_bf16 != nullptr;
+  // One wave: the pixel blocks per (image, slab) are sized so that the grid fits the CTAs this instantiation can keep
+  // resident (registers: 3 per SM for the plain variants), instead of leaving a partial second wave.
 #define TNG_GN_LAUNCH(S, P, R)                                                                                           \
-  gn_apply_kernel<S, P, R><<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, stats0, x1, dt1, x1 ? (int)C1 : 0, stats1, HW, \
-                                                          groups, tpg, slab, gamma, beta, eps,                            \
-                                                          reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off,           \
-                                                          reinterpret_cast<__nv_bfloat16*>(raw_bf16), ld_raw,             \
-                                                          raw_split_off, gn_rows)
+  do {                                                                                                                   \
+    static int per_sm = 0;                                                                                               \
+    if (per_sm == 0) {                                                                                                   \
+      int v = 0;                                                                                                         \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, gn_apply_kernel<S, P, R>, 256, 0) != cudaSuccess || v < 1)   \
+        v = 2;                                                                                                           \
+      per_sm = v;                                                                                                        \
+    }                                                                                                                    \
+    const int gn_rows = gn_rows_one_wave(NB * nslabs, HW, per_sm);                                                       \
+    dim3 grid((unsigned)((HW + gn_rows - 1) / gn_rows), (unsigned)NB, (unsigned)nslabs);                                 \
+    gn_apply_kernel<S, P, R><<<grid, 256, 0, ST(stream)>>>(x0, dt0, (int)C0, stats0, x1, dt1, x1 ? (int)C1 : 0, stats1,  \
+                                                            HW, groups, tpg, slab, gamma, beta, eps,                     \
+                                                            reinterpret_cast<__nv_bfloat16*>(y), ld_y, split_off,        \
+                                                            reinterpret_cast<__nv_bfloat16*>(raw_bf16), ld_raw,          \
+                                                            raw_split_off, gn_rows);                                     \
+  } while (0)
   if (silu) {
     if (split) { if (hasraw) TNG_GN_LAUNCH(true, true, true); else TNG_GN_LAUNCH(true, true, false); }
     else { if (hasraw) TNG_GN_LAUNCH(true, false, true); else TNG_GN_LAUNCH(true, false, false); }
